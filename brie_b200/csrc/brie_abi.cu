@@ -1,0 +1,486 @@
+// Host side of the brie_b200 C ABI (include/brie_b200.h): argument checking,
+// launch geometry, kernel dispatch.  No persistent device allocations.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/brie_b200.h"
+#include "brie_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define BRIE_CUDA(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(BRIE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace
+
+struct brie_fit {
+  brie_fit_desc d;
+  brie_fit_sizes sz;
+  brie_fit_buffers buf;
+  bool bound = false;
+  int nev_max = 0, ncell = 0;
+  size_t off_part_ev = 0, off_part_cell = 0, off_G = 0;  // scratch carve-up (float offsets)
+  float lr = 0.f;
+  int64_t t = 0;             // Adam step within the current stage
+  uint32_t global_step = 0;  // RNG step word: counts every optimisation step of the fit
+  float alpha = 0.f;
+  int64_t launches = 0;
+  bool step_open = false;    // phase 0 done, phase 1 pending
+};
+
+using namespace brie;
+
+namespace {
+
+bool kc_supported(int k) { return k == 0 || k == 1 || k == 2 || k == 4 || k == 8; }
+bool kg_supported(int k) { return k == 0 || k == 4 || k == 8; }
+
+template <int KC, int KG, bool CELL, bool LOSS>
+cudaError_t launch_step(const StepArgs& a, dim3 grid, cudaStream_t s) {
+  elbo_step_kernel<KC, KG, CELL, LOSS><<<grid, kThreads, 0, s>>>(a);
+  return cudaGetLastError();
+}
+
+template <int KC, int KG>
+cudaError_t dispatch_step2(const StepArgs& a, bool cell, bool loss, dim3 grid, cudaStream_t s) {
+  if (cell)
+    return loss ? launch_step<KC, KG, true, true>(a, grid, s) : launch_step<KC, KG, true, false>(a, grid, s);
+  return loss ? launch_step<KC, KG, false, true>(a, grid, s) : launch_step<KC, KG, false, false>(a, grid, s);
+}
+
+template <int KC>
+cudaError_t dispatch_step1(const StepArgs& a, int KG, bool cell, bool loss, dim3 grid, cudaStream_t s) {
+  switch (KG) {
+    case 0: return dispatch_step2<KC, 0>(a, cell, loss, grid, s);
+    case 4: return dispatch_step2<KC, 4>(a, cell, loss, grid, s);
+    case 8: return dispatch_step2<KC, 8>(a, cell, loss, grid, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t dispatch_step(const StepArgs& a, int KC, int KG, bool cell, bool loss, dim3 grid,
+                          cudaStream_t s) {
+  switch (KC) {
+    case 0: return dispatch_step1<0>(a, KG, cell, loss, grid, s);
+    case 1: return dispatch_step1<1>(a, KG, cell, loss, grid, s);
+    case 2: return dispatch_step1<2>(a, KG, cell, loss, grid, s);
+    case 4: return dispatch_step1<4>(a, KG, cell, loss, grid, s);
+    case 8: return dispatch_step1<8>(a, KG, cell, loss, grid, s);
+  }
+  return cudaErrorInvalidValue;
+}
+
+int grid_1d(int64_t n, int block) {
+  int64_t g = ceil_div(n, block);
+  if (g > 148 * 32) g = 148 * 32;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// bit m set iff model m still has an active event.  In shared-parameter fits
+// (cell_mode or Kg > 0) the caller deactivates whole models; for per-event fits
+// the kernels consult `active` per event and this mask stays all-ones.
+uint32_t g_all_models(const brie_fit* f) {
+  return f->d.n_models >= 32 ? 0xffffffffu : ((1u << f->d.n_models) - 1u);
+}
+
+}  // namespace
+
+extern "C" {
+
+int brie_abi_version(void) { return BRIE_ABI_VERSION; }
+
+const char* brie_last_error(void) { return g_err.c_str(); }
+
+int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
+  if (!desc || !out) return fail(BRIE_ERR_ARG, "null argument");
+  const brie_fit_desc& d = *desc;
+  if (d.n_cells <= 0 || d.n_events <= 0) return fail(BRIE_ERR_ARG, "n_cells and n_events must be positive");
+  if (d.ld < d.n_events || d.ld % 4 != 0)
+    return fail(BRIE_ERR_ARG, "ld must be a multiple of 4 and >= n_events");
+  if (d.n_cells >= ((int64_t)1 << 32) || d.event_offset < 0 || d.event_offset + d.ld >= ((int64_t)1 << 32))
+    return fail(BRIE_ERR_ARG, "cell / event index exceeds the 32-bit RNG counter words");
+  if (d.n_models < 1 || d.n_models > BRIE_MAX_MODELS) return fail(BRIE_ERR_ARG, "n_models out of range");
+  if (!kc_supported(d.Kc))
+    return fail(BRIE_ERR_UNSUPPORTED, "Kc must be one of 0,1,2,4,8 (pad Xc with zero columns)");
+  if (!kg_supported(d.Kg))
+    return fail(BRIE_ERR_UNSUPPORTED, "Kg must be one of 0,4,8 (pad Xg with zero columns)");
+  if (d.mc_size < 1 || d.mc_size > 4096) return fail(BRIE_ERR_ARG, "mc_size out of range");
+  if (d.n_layers != 2 && d.n_layers != 3) return fail(BRIE_ERR_ARG, "n_layers must be 2 or 3");
+  if (d.trace_cap < 0) return fail(BRIE_ERR_ARG, "trace_cap must be >= 0");
+  for (int m = 0; m < d.n_models; ++m) {
+    if (d.model_id[m] < 0 || d.model_id[m] >= 4096) return fail(BRIE_ERR_ARG, "model_id must be in [0, 4096)");
+    if ((d.xc_mask[m] >> d.Kc) != 0) return fail(BRIE_ERR_ARG, "xc_mask has bits beyond Kc");
+  }
+  brie_fit* f = new (std::nothrow) brie_fit();
+  if (!f) return fail(BRIE_ERR_ARG, "out of host memory");
+  f->d = d;
+  memset(&f->buf, 0, sizeof f->buf);
+  const int n_tiles = (int)ceil_div(d.ld, kTileCols);
+  // rows per CTA: enough CTAs for ~4 waves of 2 CTAs/SM when the problem allows it
+  int rows = 128;
+  const char* env = getenv("BRIE_ROWS_PER_CTA");
+  if (env && atoi(env) > 0) {
+    rows = atoi(env);
+  } else {
+    const int64_t target = 148 * 2 * 4;
+    while (rows > 8 && (int64_t)d.n_models * n_tiles * ceil_div(d.n_cells, rows) < target) rows >>= 1;
+  }
+  const int64_t n_chunks = ceil_div(d.n_cells, rows);
+  if (n_chunks > 65535 || n_tiles > 65535) {
+    delete f;
+    return fail(BRIE_ERR_UNSUPPORTED, "grid too large (%lld row chunks, %d column tiles)", (long long)n_chunks,
+                n_tiles);
+  }
+  f->nev_max = d.Kc + 2 + 2;
+  f->ncell = d.Kg + (d.cell_mode ? 2 : 0);
+  f->sz.rows_per_cta = rows;
+  f->sz.n_row_chunks = (int)n_chunks;
+  f->sz.n_col_tiles = n_tiles;
+  f->sz.reserved = 0;
+  size_t off = 0;
+  f->off_part_ev = off;
+  off += (size_t)n_chunks * d.n_models * f->nev_max * d.ld;
+  f->off_part_cell = off;
+  off += (size_t)n_tiles * d.n_models * d.n_cells * f->ncell;
+  f->off_G = off;
+  off += (size_t)d.n_models * d.n_cells * f->ncell;
+  f->sz.scratch_bytes = (off + 4) * sizeof(float);
+  f->sz.adam_small_floats =
+      (size_t)2 * d.n_models * (d.Kc + 2) * d.ld + (size_t)2 * d.n_models * d.n_cells * (d.Kg + 2);
+  *out = f;
+  return BRIE_OK;
+}
+
+int brie_fit_destroy(brie_fit* fit) {
+  delete fit;
+  return BRIE_OK;
+}
+
+int brie_fit_get_sizes(const brie_fit* fit, brie_fit_sizes* out) {
+  if (!fit || !out) return fail(BRIE_ERR_ARG, "null argument");
+  *out = fit->sz;
+  return BRIE_OK;
+}
+
+int brie_fit_bind(brie_fit* fit, const brie_fit_buffers* b) {
+  if (!fit || !b) return fail(BRIE_ERR_ARG, "null argument");
+  const brie_fit_desc& d = fit->d;
+  if (!b->counts[0] || !b->counts[1]) return fail(BRIE_ERR_ARG, "counts[0], counts[1] required");
+  if ((d.n_layers == 3) != (b->counts[2] != nullptr))
+    return fail(BRIE_ERR_ARG, "counts[2] must be given iff n_layers == 3");
+  if ((d.has_efflen != 0) != (b->efflen3 != nullptr))
+    return fail(BRIE_ERR_ARG, "efflen3 must be given iff has_efflen");
+  if (d.Kc > 0 && (!b->Xc || !b->Wc)) return fail(BRIE_ERR_ARG, "Xc and Wc required when Kc > 0");
+  if (d.Kg > 0 && (!b->Xg || !b->Wg)) return fail(BRIE_ERR_ARG, "Xg and Wg required when Kg > 0");
+  if (!b->Z_loc || !b->Z_std_log || !b->adam_Z || !b->intercept || !b->sigma_log || !b->adam_small ||
+      !b->active || !b->scratch)
+    return fail(BRIE_ERR_ARG, "missing state buffer");
+  if (d.trace_cap > 0 && !b->loss_trace) return fail(BRIE_ERR_ARG, "loss_trace required when trace_cap > 0");
+  const void* aligned[] = {b->counts[0], b->counts[1], b->counts[2], b->efflen3, b->Z_loc, b->Z_std_log,
+                           b->adam_Z,    b->Wc,        b->intercept, b->sigma_log, b->active, b->scratch};
+  for (const void* p : aligned)
+    if (((uintptr_t)p & 15u) != 0) return fail(BRIE_ERR_ARG, "device buffers must be 16-byte aligned");
+  fit->buf = *b;
+  fit->bound = true;
+  return BRIE_OK;
+}
+
+int brie_fit_init_params(brie_fit* f, float intercept_const, float sigma_const, void* stream) {
+  if (!f || !f->bound) return fail(BRIE_ERR_ARG, "fit not bound");
+  if (!(sigma_const > 0.f)) return fail(BRIE_ERR_ARG, "sigma must be positive");
+  cudaStream_t s = (cudaStream_t)stream;
+  const brie_fit_desc& d = f->d;
+  const int64_t plane = d.n_cells * d.ld;
+  const int64_t nsmall = d.cell_mode ? d.n_cells : d.ld;
+  for (int m = 0; m < d.n_models; ++m) {
+    const uint32_t mid = (uint32_t)d.model_id[m];
+    normals_kernel<<<grid_1d(plane, 256), 256, 0, s>>>(d.seed, BRIE_PHASE_INIT, mid, BRIE_INIT_Z_LOC, 1,
+                                                      d.n_cells, d.ld, d.event_offset, 0, d.ld,
+                                                      f->buf.Z_loc + m * plane);
+    normals_kernel<<<grid_1d(plane, 256), 256, 0, s>>>(d.seed, BRIE_PHASE_INIT, mid, BRIE_INIT_Z_STD_LOG, 1,
+                                                      d.n_cells, d.ld, d.event_offset, 0, d.ld,
+                                                      f->buf.Z_std_log + m * plane);
+    f->launches += 2;
+    // Wc: the reference's refit deletes the tested column (model_wrap.py:161), so its Wc has one row
+    // per USED column; compact row kk of that matrix is the kk-th set bit of xc_mask.
+    int kk = 0;
+    for (int k = 0; k < d.Kc; ++k) {
+      float* dst = f->buf.Wc + ((int64_t)m * d.Kc + k) * d.ld;
+      if ((d.xc_mask[m] >> k) & 1u) {
+        normals_kernel<<<grid_1d(d.ld, 256), 256, 0, s>>>(d.seed, BRIE_PHASE_INIT, mid, BRIE_INIT_WC, 1, 1, d.ld,
+                                                         d.event_offset, kk, d.ld, dst);
+        ++kk;
+      } else {
+        fill_kernel<<<grid_1d(d.ld, 256), 256, 0, s>>>(dst, d.ld, 0.f);
+      }
+      f->launches += 1;
+    }
+    if (d.Kg > 0) {
+      normals_kernel<<<grid_1d(d.n_cells * d.Kg, 256), 256, 0, s>>>(d.seed, BRIE_PHASE_INIT, mid, BRIE_INIT_WG, 1,
+                                                                    d.n_cells, d.Kg, 0, 0, d.Kg,
+                                                                    f->buf.Wg + (int64_t)m * d.n_cells * d.Kg);
+      f->launches += 1;
+    }
+    float* bdst = f->buf.intercept + (int64_t)m * nsmall;
+    if (d.train_intercept) {
+      if (d.cell_mode)
+        normals_kernel<<<grid_1d(d.n_cells, 256), 256, 0, s>>>(d.seed, BRIE_PHASE_INIT, mid, BRIE_INIT_INTERCEPT, 1,
+                                                              d.n_cells, 1, 0, 0, 1, bdst);
+      else
+        normals_kernel<<<grid_1d(d.ld, 256), 256, 0, s>>>(d.seed, BRIE_PHASE_INIT, mid, BRIE_INIT_INTERCEPT, 1, 1,
+                                                         d.ld, d.event_offset, 0, d.ld, bdst);
+    } else {
+      fill_kernel<<<grid_1d(nsmall, 256), 256, 0, s>>>(bdst, nsmall, intercept_const);
+    }
+    fill_kernel<<<grid_1d(nsmall, 256), 256, 0, s>>>(f->buf.sigma_log + (int64_t)m * nsmall, nsmall,
+                                                    logf(sigma_const));
+    f->launches += 2;
+  }
+  BRIE_CUDA(cudaGetLastError());
+  return BRIE_OK;
+}
+
+int brie_fit_begin_stage(brie_fit* f, float lr, void* stream) {
+  if (!f || !f->bound) return fail(BRIE_ERR_ARG, "fit not bound");
+  if (f->step_open) return fail(BRIE_ERR_ARG, "a split step is still open");
+  cudaStream_t s = (cudaStream_t)stream;
+  const brie_fit_desc& d = f->d;
+  BRIE_CUDA(cudaMemsetAsync(f->buf.adam_Z, 0, (size_t)4 * d.n_models * d.n_cells * d.ld * sizeof(float), s));
+  BRIE_CUDA(cudaMemsetAsync(f->buf.adam_small, 0, f->sz.adam_small_floats * sizeof(float), s));
+  f->lr = lr;
+  f->t = 0;
+  return BRIE_OK;
+}
+
+int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* stream) {
+  if (!f || !f->bound) return fail(BRIE_ERR_ARG, "fit not bound");
+  cudaStream_t s = (cudaStream_t)stream;
+  const brie_fit_desc& d = f->d;
+  float* scratch = (float*)f->buf.scratch;
+  const bool loss = trace_slot >= 0;
+  if (loss && trace_slot >= d.trace_cap) return fail(BRIE_ERR_ARG, "trace_slot %d >= trace_cap %d", trace_slot, d.trace_cap);
+  const int M = d.n_models;
+  const uint32_t mmask = g_all_models(f);
+  if (phase == 0) {
+    if (f->step_open) return fail(BRIE_ERR_ARG, "phase 0 called twice");
+    f->t += 1;
+    const double t = (double)f->t;
+    f->alpha = (float)((double)f->lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
+    StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.Nc = d.n_cells; a.Ng = d.n_events; a.ld = d.ld; a.event_offset = d.event_offset; a.seed = d.seed;
+    a.c[0] = f->buf.counts[0]; a.c[1] = f->buf.counts[1]; a.c[2] = f->buf.counts[2];
+    a.eff = f->buf.efflen3; a.Xc = f->buf.Xc; a.Xg = f->buf.Xg;
+    a.Zl = f->buf.Z_loc; a.Zs = f->buf.Z_std_log; a.aZ = f->buf.adam_Z;
+    a.Wc = f->buf.Wc; a.b = f->buf.intercept; a.tau = f->buf.sigma_log; a.Wg = f->buf.Wg;
+    a.active = f->buf.active;
+    a.part_ev = scratch + f->off_part_ev;
+    a.part_cell = scratch + f->off_part_cell;
+    a.alpha = f->alpha;
+    a.inv_S = 1.0f / (float)d.mc_size;
+    a.step = f->global_step;
+    a.model_mask = mmask;
+    a.M = M; a.S = d.mc_size; a.rows_per_cta = f->sz.rows_per_cta;
+    for (int m = 0; m < M; ++m) a.model_id[m] = d.model_id[m];
+    const dim3 grid(M, f->sz.n_col_tiles, f->sz.n_row_chunks);
+    BRIE_CUDA(dispatch_step(a, d.Kc, d.Kg, d.cell_mode != 0, loss, grid, s));
+    f->launches += 1;
+
+    const int nev = d.Kc + (d.cell_mode ? 0 : 2) + (loss ? 2 : 0);
+    if (nev > 0) {
+      EventArgs e;
+      memset(&e, 0, sizeof e);
+      e.ld = d.ld; e.Ng = d.n_events; e.M = M; e.KC = d.Kc; e.NEV = nev; e.n_chunks = f->sz.n_row_chunks;
+      e.idx_gb = d.cell_mode ? -1 : d.Kc;
+      e.idx_gt = d.cell_mode ? -1 : d.Kc + 1;
+      e.idx_kl = loss ? d.Kc + (d.cell_mode ? 0 : 2) : -1;
+      e.train_b = d.train_intercept; e.train_tau = d.train_sigma;
+      e.trace_slot = trace_slot; e.trace_cap = d.trace_cap;
+      e.alpha = f->alpha;
+      e.part_ev = scratch + f->off_part_ev;
+      e.Wc = f->buf.Wc; e.b = f->buf.intercept; e.tau = f->buf.sigma_log;
+      e.mom = f->buf.adam_small;
+      e.active = f->buf.active;
+      e.trace = f->buf.loss_trace;
+      for (int m = 0; m < M; ++m) e.xc_mask[m] = d.xc_mask[m];
+      const dim3 g2((unsigned)ceil_div(d.n_events, 256), M);
+      event_update_kernel<<<g2, 256, 0, s>>>(e);
+      BRIE_CUDA(cudaGetLastError());
+      f->launches += 1;
+    }
+    if (f->ncell > 0) {
+      CellArgs c;
+      memset(&c, 0, sizeof c);
+      c.Nc = d.n_cells; c.M = M; c.KG = d.Kg; c.NCELL = f->ncell; c.n_tiles = f->sz.n_col_tiles;
+      c.model_mask = mmask;
+      c.part_cell = scratch + f->off_part_cell;
+      c.G = scratch + f->off_G;
+      const dim3 g3((unsigned)ceil_div(d.n_cells * f->ncell, 256), M);
+      cell_reduce_kernel<<<g3, 256, 0, s>>>(c);
+      BRIE_CUDA(cudaGetLastError());
+      f->launches += 1;
+    }
+    f->step_open = true;
+    return BRIE_OK;
+  }
+  if (phase == 1) {
+    if (!f->step_open) return fail(BRIE_ERR_ARG, "phase 1 without phase 0");
+    if (f->ncell > 0) {
+      CellArgs c;
+      memset(&c, 0, sizeof c);
+      c.Nc = d.n_cells; c.M = M; c.KG = d.Kg; c.NCELL = f->ncell; c.n_tiles = f->sz.n_col_tiles;
+      c.cell_mode = d.cell_mode; c.train_b = d.train_intercept; c.train_tau = d.train_sigma;
+      c.model_mask = mmask;
+      c.alpha = f->alpha;
+      c.G = scratch + f->off_G;
+      c.Wg = f->buf.Wg; c.b = f->buf.intercept; c.tau = f->buf.sigma_log;
+      c.mom = f->buf.adam_small + (size_t)2 * M * (d.Kc + 2) * d.ld;
+      const dim3 g4((unsigned)ceil_div(d.n_cells, 256), M);
+      cell_update_kernel<<<g4, 256, 0, s>>>(c);
+      BRIE_CUDA(cudaGetLastError());
+      f->launches += 1;
+    }
+    f->global_step += 1;
+    f->step_open = false;
+    return BRIE_OK;
+  }
+  return fail(BRIE_ERR_ARG, "phase must be 0 or 1");
+}
+
+int brie_fit_run_steps(brie_fit* f, int32_t n_steps, int32_t trace_slot0, void* stream) {
+  if (!f || !f->bound) return fail(BRIE_ERR_ARG, "fit not bound");
+  if (n_steps < 0) return fail(BRIE_ERR_ARG, "n_steps must be >= 0");
+  for (int i = 0; i < n_steps; ++i) {
+    const int slot = trace_slot0 >= 0 ? trace_slot0 + i : -1;
+    int rc = brie_fit_step_phase(f, 0, slot, stream);
+    if (rc) return rc;
+    rc = brie_fit_step_phase(f, 1, slot, stream);
+    if (rc) return rc;
+  }
+  return BRIE_OK;
+}
+
+int brie_fit_cell_grad(brie_fit* f, float** ptr, int64_t* n_floats) {
+  if (!f || !f->bound || !ptr || !n_floats) return fail(BRIE_ERR_ARG, "null argument or fit not bound");
+  *ptr = (float*)f->buf.scratch + f->off_G;
+  *n_floats = (int64_t)f->d.n_models * f->d.n_cells * f->ncell;
+  return BRIE_OK;
+}
+
+int brie_fit_eval_loss_gene(brie_fit* f, int32_t n_eval, float* loss_gene, void* stream) {
+  if (!f || !f->bound || !loss_gene) return fail(BRIE_ERR_ARG, "null argument or fit not bound");
+  if (n_eval < 1) return fail(BRIE_ERR_ARG, "n_eval must be >= 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  const brie_fit_desc& d = f->d;
+  float* scratch = (float*)f->buf.scratch;
+  EvalArgs a;
+  memset(&a, 0, sizeof a);
+  a.Nc = d.n_cells; a.Ng = d.n_events; a.ld = d.ld; a.event_offset = d.event_offset; a.seed = d.seed;
+  a.c[0] = f->buf.counts[0]; a.c[1] = f->buf.counts[1]; a.c[2] = f->buf.counts[2];
+  a.eff = f->buf.efflen3; a.Xc = f->buf.Xc; a.Xg = f->buf.Xg;
+  a.Zl = f->buf.Z_loc; a.Zs = f->buf.Z_std_log;
+  a.Wc = f->buf.Wc; a.b = f->buf.intercept; a.tau = f->buf.sigma_log; a.Wg = f->buf.Wg;
+  a.part_ev = scratch + f->off_part_ev;
+  a.M = d.n_models; a.S = d.mc_size; a.n_eval = n_eval; a.rows_per_cta = f->sz.rows_per_cta;
+  a.KC = d.Kc; a.KG = d.Kg; a.cell_mode = d.cell_mode;
+  for (int m = 0; m < d.n_models; ++m) a.model_id[m] = d.model_id[m];
+  const dim3 grid(d.n_models, f->sz.n_col_tiles, f->sz.n_row_chunks);
+  eval_loss_kernel<<<grid, kThreads, 0, s>>>(a);
+  BRIE_CUDA(cudaGetLastError());
+  const dim3 g2((unsigned)ceil_div(d.ld, 256), d.n_models);
+  eval_reduce_kernel<<<g2, 256, 0, s>>>(a.part_ev, f->sz.n_row_chunks, d.n_models, d.ld, d.n_events, loss_gene);
+  BRIE_CUDA(cudaGetLastError());
+  f->launches += 2;
+  return BRIE_OK;
+}
+
+int brie_fit_posterior(brie_fit* f, int32_t model, float* Psi, float* Psi95CI, float* Z_std, void* stream) {
+  if (!f || !f->bound) return fail(BRIE_ERR_ARG, "fit not bound");
+  if (model < 0 || model >= f->d.n_models) return fail(BRIE_ERR_ARG, "model index out of range");
+  const int64_t plane = f->d.n_cells * f->d.ld;
+  posterior_kernel<<<grid_1d(plane, 256), 256, 0, (cudaStream_t)stream>>>(
+      f->buf.Z_loc + model * plane, f->buf.Z_std_log + model * plane, plane, Psi, Psi95CI, Z_std);
+  BRIE_CUDA(cudaGetLastError());
+  f->launches += 1;
+  return BRIE_OK;
+}
+
+int brie_fit_group_trace(brie_fit* f, int32_t n_slots, int64_t group_size, int64_t n_groups, double* out,
+                         void* stream) {
+  if (!f || !f->bound || !out) return fail(BRIE_ERR_ARG, "null argument or fit not bound");
+  const brie_fit_desc& d = f->d;
+  if (n_slots < 1 || n_slots > d.trace_cap) return fail(BRIE_ERR_ARG, "n_slots out of range");
+  if (group_size < 1 || n_groups < 1) return fail(BRIE_ERR_ARG, "bad group geometry");
+  const int64_t first_group = d.event_offset / group_size;
+  const dim3 grid(n_slots, d.n_models);
+  group_trace_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(f->buf.loss_trace, d.trace_cap, d.ld, d.n_events,
+                                                           d.event_offset, group_size, first_group, n_groups,
+                                                           n_slots, out);
+  BRIE_CUDA(cudaGetLastError());
+  f->launches += 1;
+  return BRIE_OK;
+}
+
+int64_t brie_fit_launch_count(const brie_fit* f) { return f ? f->launches : -1; }
+
+int brie_philox_normals_host(uint64_t seed, uint32_t phase, uint32_t model, uint32_t step, int32_t n_samples,
+                             int64_t n_rows, int64_t n_cols, int64_t col_offset, float* out) {
+  if (!out || n_samples < 1 || n_rows < 0 || n_cols < 0) return fail(BRIE_ERR_ARG, "bad argument");
+  for (int64_t r = 0; r < n_rows; ++r)
+    for (int64_t c = 0; c < n_cols; ++c)
+      for (int s0 = 0; s0 < n_samples; s0 += 4) {
+        float e[4];
+        brie_normals4((uint32_t)(col_offset + c), (uint32_t)r, step, brie_stream_word(phase, model, (uint32_t)(s0 >> 2)),
+                      seed, e);
+        for (int q = 0; q < 4 && s0 + q < n_samples; ++q) out[((int64_t)(s0 + q) * n_rows + r) * n_cols + c] = e[q];
+      }
+  return BRIE_OK;
+}
+
+int brie_philox_normals_device(uint64_t seed, uint32_t phase, uint32_t model, uint32_t step, int32_t n_samples,
+                               int64_t n_rows, int64_t n_cols, int64_t col_offset, float* out, void* stream) {
+  if (!out || n_samples < 1 || n_rows < 0 || n_cols < 0) return fail(BRIE_ERR_ARG, "bad argument");
+  normals_kernel<<<grid_1d(n_rows * n_cols, 256), 256, 0, (cudaStream_t)stream>>>(
+      seed, phase, model, step, n_samples, n_rows, n_cols, col_offset, 0, n_cols, out);
+  BRIE_CUDA(cudaGetLastError());
+  return BRIE_OK;
+}
+
+int brie_simulate_counts(uint64_t seed, int64_t n_cells, int64_t n_events, int64_t ld, int64_t event_offset,
+                         const float* logit_mean, const float* logit_sd, const float* Xc, const float* Wc,
+                         int32_t Kc, const float* efflen3, const float* lam, const float* cdr, float pseudo_count,
+                         float* c1, float* c2, float* c3, void* stream) {
+  (void)seed; (void)n_cells; (void)n_events; (void)ld; (void)event_offset; (void)logit_mean; (void)logit_sd;
+  (void)Xc; (void)Wc; (void)Kc; (void)efflen3; (void)lam; (void)cdr; (void)pseudo_count; (void)c1; (void)c2;
+  (void)c3; (void)stream;
+  return fail(BRIE_ERR_UNSUPPORTED, "brie_simulate_counts: not implemented yet");
+}
+
+}  // extern "C"

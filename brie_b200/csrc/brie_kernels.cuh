@@ -1,0 +1,636 @@
+// Device kernels of the BRIE2 variational fit for sm_100a.
+//
+// Hot path replaced: one optimisation step of `tfp.math.minimize` over
+// BRIE2.get_loss (brie/models/model_TFProb.py:194-211, 130-191, 118-127) plus the
+// keras Adam update and the Variable constraints (:68-69, :80-81).  The reference
+// materialises ~17 (S,Nc,Ng[,3]) tensors forward and as many backward; here one
+// pass over the (cells, events) state does sampling, likelihood, KL, analytic
+// gradients and Adam, reading 24 B + writing 24 B of state and reading 12 B of
+// counts per cell x event (HBM-bound).
+//
+// Layout: every (cells, events) array is row-major, events contiguous, leading
+// dimension ld (ld % 4 == 0).  A warp owns a 128-event row segment (lane = 4
+// consecutive events, one 16-byte load per array), a CTA of 8 warps owns
+// rows_per_cta x 128 and walks its rows warp-interleaved.  Per-event sums over
+// cells live in registers and leave the CTA as one partial per row chunk
+// (deterministic two-stage reduction, no atomics); per-cell sums over events
+// (gene-feature weights, per-cell intercept/sigma) are warp-shuffle reduced per
+// row and leave as one partial per column tile.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "brie_philox.h"
+
+namespace brie {
+
+constexpr int kTileCols = 128;  // events per warp row segment
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxModels = 32;
+
+constexpr float kB1c = 0.1f;     // 1 - beta_1 (keras Adam)
+constexpr float kB2c = 0.001f;   // 1 - beta_2
+constexpr float kAdamEps = 1e-7f;
+constexpr float kZ975 = 1.959963984540054f;
+
+struct StepArgs {
+  int64_t Nc, Ng, ld, event_offset;
+  uint64_t seed;
+  const float* c[3];
+  const float* eff;  // (3, ld) or null
+  const float* Xc;   // (Nc, KC)
+  const float* Xg;   // (Ng, KG)
+  float* Zl;         // (M, Nc, ld)
+  float* Zs;
+  float* aZ;         // (4, M, Nc, ld)
+  const float* Wc;   // (M, KC, ld)
+  const float* b;    // (M, ld) | (M, Nc)
+  const float* tau;
+  const float* Wg;   // (M, Nc, KG)
+  const uint8_t* active;  // (M, ld)
+  float* part_ev;    // (n_row_chunks, M, NEV, ld)
+  float* part_cell;  // (n_col_tiles, M, Nc, NCELL)
+  float alpha;
+  float inv_S;
+  uint32_t step;
+  uint32_t model_mask;  // bit m: model m has any active event
+  int32_t M, S, rows_per_cta;
+  int32_t model_id[kMaxModels];
+};
+
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float y;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// keras Adam update_step (TF 2.15): m += (g-m)(1-b1); v += (g^2-v)(1-b2);
+// x -= alpha_t * m / (sqrt(v) + eps)
+__device__ __forceinline__ void adam_update(float& x, float& m, float& v, float g, float alpha) {
+  m = fmaf(g - m, kB1c, m);
+  v = fmaf(fmaf(g, g, -v), kB2c, v);
+  x -= (m * alpha) * rcp_approx(sqrt_approx(v) + kAdamEps);
+}
+
+__device__ __forceinline__ float clip9(float x) { return fminf(fmaxf(x, -9.0f), 9.0f); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// MC part of one element: S reparameterised samples z = mu + s*eps, the isoform
+// likelihood of logLik_MC (model_TFProb.py:159-185) in the form
+//   l = c1 log psi + c2 log(1-psi) + [c1 log L1 + c2 log L2 + c3 log L3] - n log D,
+//   D = psi L1 + (1-psi) L2 + L3   (the binomial branch :162-167 is L = (1,1,0))
+// and dl/dz = c1(1-psi) - c2 psi - n psi(1-psi)(L1-L2)/D.
+// Returns sum_s g, sum_s g*eps and (LOSS) sum_s l without the bracket.
+template <bool LOSS>
+__device__ __forceinline__ void mc_samples(float mu, float s, float c1, float c2, float n,
+                                           float L1, float L2, float L3, float dL, int S,
+                                           uint32_t event, uint32_t cell, uint32_t step,
+                                           uint32_t stream0, uint64_t seed, float& gsum,
+                                           float& gesum, float& llsum) {
+  gsum = 0.f; gesum = 0.f; llsum = 0.f;
+  for (int s0 = 0; s0 < S; s0 += 4) {
+    float eps[4];
+    brie_normals4(event, cell, step, stream0 + (uint32_t)(s0 >> 2), seed, eps);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (s0 + j < S) {
+        const float z = fmaf(s, eps[j], mu);
+        const float e = __expf(-fabsf(z));
+        const float inv = rcp_approx(1.0f + e);
+        const float lo = e * inv;
+        const float psi = z >= 0.f ? inv : lo;
+        const float q = z >= 0.f ? lo : inv;
+        const float D = fmaf(psi, L1, fmaf(q, L2, L3));
+        const float g = fmaf(c1, q, -c2 * psi) - n * psi * q * dL * rcp_approx(D);
+        gsum += g;
+        gesum = fmaf(g, eps[j], gesum);
+        if (LOSS) {
+          const float lsp = fminf(z, 0.f) - __logf(1.0f + e);  // log sigmoid(z)
+          llsum += fmaf(c1, lsp, c2 * (lsp - z)) - n * __logf(D);
+        }
+      }
+    }
+  }
+}
+
+template <int KC, int KG, bool CELL, bool LOSS>
+struct StepTraits {
+  static constexpr int kGB = KC;                       // index of d/d intercept (gene mode)
+  static constexpr int kGT = KC + 1;                   // index of d/d sigma_log (gene mode)
+  static constexpr int kKL = KC + (CELL ? 0 : 2);      // KL sum
+  static constexpr int kLL = kKL + 1;                  // log-lik sum
+  static constexpr int NEV = KC + (CELL ? 0 : 2) + (LOSS ? 2 : 0);
+  static constexpr int NCELL = KG + (CELL ? 2 : 0);
+};
+
+// Fused ELBO forward + backward + Adam for the per-element variables.
+// grid = (M, n_col_tiles, n_row_chunks): models fastest so the CTAs sharing a
+// count tile are co-resident and the counts are fetched from HBM once.
+template <int KC, int KG, bool CELL, bool LOSS>
+__global__ void __launch_bounds__(kThreads, 2) elbo_step_kernel(const StepArgs a) {
+  using T = StepTraits<KC, KG, CELL, LOSS>;
+  constexpr int NEV = T::NEV;
+  constexpr int NCELL = T::NCELL;
+  const int m = blockIdx.x;
+  if (!((a.model_mask >> m) & 1u)) return;
+  const int tile = blockIdx.y;
+  const int chunk = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t g0 = (int64_t)tile * kTileCols + lane * 4;
+  const bool in_ld = g0 < a.ld;
+
+  uint32_t act4 = 0;
+  if (in_ld) act4 = *reinterpret_cast<const uint32_t*>(a.active + (int64_t)m * a.ld + g0);
+  if (!__syncthreads_or(act4 != 0)) return;
+
+  bool act[4], valid[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    act[j] = (act4 >> (8 * j)) & 0xffu;
+    valid[j] = (g0 + j) < a.Ng;
+  }
+
+  // per-event constants (registers)
+  float L1[4], L2[4], L3[4], dL[4], K1[4], K2[4], K3[4];
+  float wc[KC > 0 ? KC : 1][4];
+  float xg[KG > 0 ? KG : 1][4];
+  float bb[4], tau[4], is2[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    L1[j] = 1.f; L2[j] = 1.f; L3[j] = 0.f; bb[j] = 0.f; tau[j] = 0.f; is2[j] = 1.f;
+    K1[j] = K2[j] = K3[j] = 0.f;
+  }
+  if (in_ld) {
+    if (a.eff) {
+      const float4 v1 = *reinterpret_cast<const float4*>(a.eff + g0);
+      const float4 v2 = *reinterpret_cast<const float4*>(a.eff + a.ld + g0);
+      const float4 v3 = *reinterpret_cast<const float4*>(a.eff + 2 * a.ld + g0);
+      L1[0] = v1.x; L1[1] = v1.y; L1[2] = v1.z; L1[3] = v1.w;
+      L2[0] = v2.x; L2[1] = v2.y; L2[2] = v2.z; L2[3] = v2.w;
+      L3[0] = v3.x; L3[1] = v3.y; L3[2] = v3.z; L3[3] = v3.w;
+      if (LOSS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          K1[j] = logf(L1[j]); K2[j] = logf(L2[j]); K3[j] = logf(L3[j]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KC; ++k) {
+      const float4 v = *reinterpret_cast<const float4*>(a.Wc + ((int64_t)m * KC + k) * a.ld + g0);
+      wc[k][0] = v.x; wc[k][1] = v.y; wc[k][2] = v.z; wc[k][3] = v.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int k = 0; k < KG; ++k) xg[k][j] = valid[j] ? a.Xg[(g0 + j) * KG + k] : 0.f;
+    }
+    if (!CELL) {
+      const float4 vb = *reinterpret_cast<const float4*>(a.b + (int64_t)m * a.ld + g0);
+      const float4 vt = *reinterpret_cast<const float4*>(a.tau + (int64_t)m * a.ld + g0);
+      bb[0] = vb.x; bb[1] = vb.y; bb[2] = vb.z; bb[3] = vb.w;
+      tau[0] = vt.x; tau[1] = vt.y; tau[2] = vt.z; tau[3] = vt.w;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) is2[j] = __expf(-2.0f * tau[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) dL[j] = L1[j] - L2[j];
+
+  float acc[NEV > 0 ? NEV : 1][4];
+#pragma unroll
+  for (int i = 0; i < (NEV > 0 ? NEV : 1); ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int64_t row_begin = (int64_t)chunk * a.rows_per_cta;
+  const int64_t row_end = min(row_begin + (int64_t)a.rows_per_cta, a.Nc);
+  const int64_t plane = a.Nc * a.ld;
+  const uint32_t stream0 = brie_stream_word(BRIE_PHASE_TRAIN, (uint32_t)a.model_id[m], 0u);
+  const bool has_c3 = a.c[2] != nullptr;
+
+  for (int64_t row = row_begin + warp; row < row_end; row += kWarps) {
+    const int64_t off = row * a.ld + g0;          // into one (Nc, ld) plane
+    const int64_t moff = (int64_t)m * plane + off; // into a (M, Nc, ld) array
+    float mu[4], lam[4], m1[4], v1[4], m2[4], v2[4], c1[4], c2[4], c3[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { mu[j] = lam[j] = m1[j] = v1[j] = m2[j] = v2[j] = c1[j] = c2[j] = c3[j] = 0.f; }
+    if (in_ld) {
+      const float4 t0 = __ldcs(reinterpret_cast<const float4*>(a.Zl + moff));
+      const float4 t1 = __ldcs(reinterpret_cast<const float4*>(a.Zs + moff));
+      const float4 t2 = __ldcs(reinterpret_cast<const float4*>(a.aZ + 0 * a.M * plane + moff));
+      const float4 t3 = __ldcs(reinterpret_cast<const float4*>(a.aZ + 1 * a.M * plane + moff));
+      const float4 t4 = __ldcs(reinterpret_cast<const float4*>(a.aZ + 2 * a.M * plane + moff));
+      const float4 t5 = __ldcs(reinterpret_cast<const float4*>(a.aZ + 3 * a.M * plane + moff));
+      const float4 t6 = __ldg(reinterpret_cast<const float4*>(a.c[0] + off));
+      const float4 t7 = __ldg(reinterpret_cast<const float4*>(a.c[1] + off));
+      float4 t8 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_c3) t8 = __ldg(reinterpret_cast<const float4*>(a.c[2] + off));
+      mu[0] = t0.x; mu[1] = t0.y; mu[2] = t0.z; mu[3] = t0.w;
+      lam[0] = t1.x; lam[1] = t1.y; lam[2] = t1.z; lam[3] = t1.w;
+      m1[0] = t2.x; m1[1] = t2.y; m1[2] = t2.z; m1[3] = t2.w;
+      v1[0] = t3.x; v1[1] = t3.y; v1[2] = t3.z; v1[3] = t3.w;
+      m2[0] = t4.x; m2[1] = t4.y; m2[2] = t4.z; m2[3] = t4.w;
+      v2[0] = t5.x; v2[1] = t5.y; v2[2] = t5.z; v2[3] = t5.w;
+      c1[0] = t6.x; c1[1] = t6.y; c1[2] = t6.z; c1[3] = t6.w;
+      c2[0] = t7.x; c2[1] = t7.y; c2[2] = t7.z; c2[3] = t7.w;
+      c3[0] = t8.x; c3[1] = t8.y; c3[2] = t8.z; c3[3] = t8.w;
+    }
+    // per-row (cell) constants: warp-uniform loads
+    float xc[KC > 0 ? KC : 1];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) xc[k] = __ldg(a.Xc + row * KC + k);
+    float wg[KG > 0 ? KG : 1];
+#pragma unroll
+    for (int k = 0; k < KG; ++k) wg[k] = __ldg(a.Wg + ((int64_t)m * a.Nc + row) * KG + k);
+    float b_row = 0.f, tau_row = 0.f, is2_row = 1.f;
+    if (CELL) {
+      b_row = __ldg(a.b + (int64_t)m * a.Nc + row);
+      tau_row = __ldg(a.tau + (int64_t)m * a.Nc + row);
+      is2_row = __expf(-2.0f * tau_row);
+    }
+    float cacc[NCELL > 0 ? NCELL : 1];
+#pragma unroll
+    for (int i = 0; i < (NCELL > 0 ? NCELL : 1); ++i) cacc[i] = 0.f;
+
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float tj = CELL ? tau_row : tau[j];
+      const float i2 = CELL ? is2_row : is2[j];
+      float pm = CELL ? b_row : bb[j];
+#pragma unroll
+      for (int k = 0; k < KC; ++k) pm = fmaf(xc[k], wc[k][j], pm);
+#pragma unroll
+      for (int k = 0; k < KG; ++k) pm = fmaf(wg[k], xg[k][j], pm);
+      const float d = lam[j] - tj;
+      const float e2 = __expf(2.0f * d);            // s^2 / sigma^2
+      const float diff = mu[j] - pm;
+      const float r = diff * i2;                    // (mu - m) / sigma^2
+      const float q2 = diff * r;                    // ((mu - m) / sigma)^2
+      float gmu = r;
+      float glam = e2 - 1.0f;
+      float ll = 0.f;
+      const float n = c1[j] + c2[j] + c3[j];
+      if (n > 0.f) {
+        const float s = __expf(lam[j]);
+        float gs, ge, ls;
+        mc_samples<LOSS>(mu[j], s, c1[j], c2[j], n, L1[j], L2[j], L3[j], dL[j], a.S,
+                         (uint32_t)(a.event_offset + g0 + j), (uint32_t)row, a.step, stream0,
+                         a.seed, gs, ge, ls);
+        gmu = fmaf(-a.inv_S, gs, gmu);
+        glam = fmaf(-a.inv_S * s, ge, glam);
+        if (LOSS) ll = fmaf(a.inv_S, ls, fmaf(c1[j], K1[j], fmaf(c2[j], K2[j], c3[j] * K3[j])));
+      }
+      // accumulate shared-parameter gradients and loss terms (pre-update values)
+      const float gt = 1.0f - q2 - e2;              // d loss / d sigma_log
+#pragma unroll
+      for (int k = 0; k < KC; ++k) acc[k][j] = fmaf(-xc[k], r, acc[k][j]);
+      if (!CELL) {
+        acc[T::kGB][j] -= r;
+        acc[T::kGT][j] += gt;
+      }
+      if (LOSS) {
+        acc[T::kKL][j] += 0.5f * q2 + 0.5f * (e2 - 1.0f) - d;  // TFP _kl_normal_normal
+        acc[T::kLL][j] += ll;
+      }
+      if (NCELL > 0 && valid[j]) {
+#pragma unroll
+        for (int k = 0; k < KG; ++k) cacc[k] = fmaf(-xg[k][j], r, cacc[k]);
+        if (CELL) {
+          cacc[KG] -= r;
+          cacc[KG + 1] += gt;
+        }
+      }
+      if (act[j]) {
+        adam_update(mu[j], m1[j], v1[j], gmu, a.alpha);
+        adam_update(lam[j], m2[j], v2[j], glam, a.alpha);
+        mu[j] = clip9(mu[j]);                       // Variable constraint (model_TFProb.py:80-81)
+      }
+    }
+    if (in_ld && act4 != 0) {
+      __stcs(reinterpret_cast<float4*>(a.Zl + moff), make_float4(mu[0], mu[1], mu[2], mu[3]));
+      __stcs(reinterpret_cast<float4*>(a.Zs + moff), make_float4(lam[0], lam[1], lam[2], lam[3]));
+      __stcs(reinterpret_cast<float4*>(a.aZ + 0 * a.M * plane + moff), make_float4(m1[0], m1[1], m1[2], m1[3]));
+      __stcs(reinterpret_cast<float4*>(a.aZ + 1 * a.M * plane + moff), make_float4(v1[0], v1[1], v1[2], v1[3]));
+      __stcs(reinterpret_cast<float4*>(a.aZ + 2 * a.M * plane + moff), make_float4(m2[0], m2[1], m2[2], m2[3]));
+      __stcs(reinterpret_cast<float4*>(a.aZ + 3 * a.M * plane + moff), make_float4(v2[0], v2[1], v2[2], v2[3]));
+    }
+    if (NCELL > 0) {
+#pragma unroll
+      for (int i = 0; i < NCELL; ++i) {
+        const float s = warp_sum(cacc[i]);
+        if (lane == 0)
+          a.part_cell[(((int64_t)tile * a.M + m) * a.Nc + row) * NCELL + i] = s;
+      }
+    }
+  }
+
+  if (NEV > 0) {
+    __shared__ float red[kWarps][kTileCols];
+    const int64_t gcol = (int64_t)tile * kTileCols + threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < NEV; ++i) {
+      *reinterpret_cast<float4*>(&red[warp][lane * 4]) =
+          make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      __syncthreads();
+      if (threadIdx.x < kTileCols && gcol < a.ld) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
+        a.part_ev[(((int64_t)chunk * a.M + m) * NEV + i) * a.ld + gcol] = s;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// Per-event finalize: reduce the row-chunk partials in fixed order, Adam on Wc /
+// per-event intercept / sigma_log (keras Adam + clip, model_TFProb.py:68-69), and
+// write the pre-update per-event loss  sum_c KL - sum_c loglik  (:207-211).
+struct EventArgs {
+  int64_t ld, Ng;
+  int32_t M, KC, NEV, n_chunks;
+  int32_t idx_gb, idx_gt, idx_kl;  // -1 if absent
+  int32_t train_b, train_tau, trace_slot, trace_cap;
+  float alpha;
+  const float* part_ev;
+  float* Wc; float* b; float* tau;
+  float* mom;          // (2, M, KC + 2, ld)
+  const uint8_t* active;
+  float* trace;
+  uint32_t xc_mask[kMaxModels];
+};
+
+__global__ void __launch_bounds__(256) event_update_kernel(const EventArgs a) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (g >= a.Ng) return;
+  if (!a.active[(int64_t)m * a.ld + g]) return;
+  const int64_t mstride = (int64_t)a.M * (a.KC + 2) * a.ld;
+  auto red = [&](int i) {
+    double s = 0.0;
+    for (int c = 0; c < a.n_chunks; ++c)
+      s += (double)a.part_ev[(((int64_t)c * a.M + m) * a.NEV + i) * a.ld + g];
+    return s;
+  };
+  for (int k = 0; k < a.KC; ++k) {
+    if (!((a.xc_mask[m] >> k) & 1u)) continue;
+    const float grad = (float)red(k);
+    const int64_t pi = ((int64_t)m * a.KC + k) * a.ld + g;
+    const int64_t qi = ((int64_t)m * (a.KC + 2) + k) * a.ld + g;
+    float x = a.Wc[pi], mm = a.mom[qi], vv = a.mom[mstride + qi];
+    adam_update(x, mm, vv, grad, a.alpha);
+    a.Wc[pi] = x; a.mom[qi] = mm; a.mom[mstride + qi] = vv;
+  }
+  if (a.idx_gb >= 0 && a.train_b) {
+    const float grad = (float)red(a.idx_gb);
+    const int64_t pi = (int64_t)m * a.ld + g;
+    const int64_t qi = ((int64_t)m * (a.KC + 2) + a.KC) * a.ld + g;
+    float x = a.b[pi], mm = a.mom[qi], vv = a.mom[mstride + qi];
+    adam_update(x, mm, vv, grad, a.alpha);
+    a.b[pi] = clip9(x); a.mom[qi] = mm; a.mom[mstride + qi] = vv;
+  }
+  if (a.idx_gt >= 0 && a.train_tau) {
+    const float grad = (float)red(a.idx_gt);
+    const int64_t pi = (int64_t)m * a.ld + g;
+    const int64_t qi = ((int64_t)m * (a.KC + 2) + a.KC + 1) * a.ld + g;
+    float x = a.tau[pi], mm = a.mom[qi], vv = a.mom[mstride + qi];
+    adam_update(x, mm, vv, grad, a.alpha);
+    a.tau[pi] = x; a.mom[qi] = mm; a.mom[mstride + qi] = vv;
+  }
+  if (a.idx_kl >= 0 && a.trace_slot >= 0) {
+    const double kl = red(a.idx_kl), ll = red(a.idx_kl + 1);
+    a.trace[((int64_t)m * a.trace_cap + a.trace_slot) * a.ld + g] = (float)(kl - ll);
+  }
+}
+
+// Per-cell gradient reduce over column tiles: G[m, c, i] = sum_tiles part_cell.
+struct CellArgs {
+  int64_t Nc;
+  int32_t M, KG, NCELL, n_tiles;
+  int32_t cell_mode, train_b, train_tau;
+  uint32_t model_mask;
+  float alpha;
+  const float* part_cell;
+  float* G;            // (M, Nc, NCELL)
+  float* Wg; float* b; float* tau;
+  float* mom;          // (2, M, Nc, KG + 2)
+};
+
+__global__ void __launch_bounds__(256) cell_reduce_kernel(const CellArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over Nc * NCELL
+  const int m = blockIdx.y;
+  if (i >= a.Nc * a.NCELL) return;
+  if (!((a.model_mask >> m) & 1u)) return;
+  double s = 0.0;
+  for (int t = 0; t < a.n_tiles; ++t)
+    s += (double)a.part_cell[((int64_t)t * a.M + m) * a.Nc * a.NCELL + i];
+  a.G[(int64_t)m * a.Nc * a.NCELL + i] = (float)s;
+}
+
+__global__ void __launch_bounds__(256) cell_update_kernel(const CellArgs a) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (c >= a.Nc) return;
+  if (!((a.model_mask >> m) & 1u)) return;
+  const float* G = a.G + ((int64_t)m * a.Nc + c) * a.NCELL;
+  const int64_t mstride = (int64_t)a.M * a.Nc * (a.KG + 2);
+  float* mom = a.mom + ((int64_t)m * a.Nc + c) * (a.KG + 2);
+  for (int k = 0; k < a.KG; ++k) {
+    float x = a.Wg[((int64_t)m * a.Nc + c) * a.KG + k], mm = mom[k], vv = mom[mstride + k];
+    adam_update(x, mm, vv, G[k], a.alpha);
+    a.Wg[((int64_t)m * a.Nc + c) * a.KG + k] = x; mom[k] = mm; mom[mstride + k] = vv;
+  }
+  if (a.cell_mode) {
+    if (a.train_b) {
+      float x = a.b[(int64_t)m * a.Nc + c], mm = mom[a.KG], vv = mom[mstride + a.KG];
+      adam_update(x, mm, vv, G[a.KG], a.alpha);
+      a.b[(int64_t)m * a.Nc + c] = clip9(x); mom[a.KG] = mm; mom[mstride + a.KG] = vv;
+    }
+    if (a.train_tau) {
+      float x = a.tau[(int64_t)m * a.Nc + c], mm = mom[a.KG + 1], vv = mom[mstride + a.KG + 1];
+      adam_update(x, mm, vv, G[a.KG + 1], a.alpha);
+      a.tau[(int64_t)m * a.Nc + c] = x; mom[a.KG + 1] = mm; mom[mstride + a.KG + 1] = vv;
+    }
+  }
+}
+
+// Forward-only per-event loss with n_eval x S fresh-noise samples per element
+// (the 500x get_loss(axis=0) loop of model_TFProb.py:261-264 in one pass).  Only
+// elements with reads need samples: a zero-count element's log-lik is 0 for any z.
+// IEEE-accurate math (this value feeds ELBO_gain, model_wrap.py:183-185).
+struct EvalArgs {
+  int64_t Nc, Ng, ld, event_offset;
+  uint64_t seed;
+  const float* c[3];
+  const float* eff;
+  const float* Xc; const float* Xg;
+  const float* Zl; const float* Zs;
+  const float* Wc; const float* b; const float* tau; const float* Wg;
+  float* part_ev;      // (n_row_chunks, M, 2, ld)
+  int32_t M, S, n_eval, rows_per_cta, KC, KG, cell_mode;
+  int32_t model_id[kMaxModels];
+};
+
+__global__ void __launch_bounds__(kThreads) eval_loss_kernel(const EvalArgs a) {
+  const int m = blockIdx.x, tile = blockIdx.y, chunk = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t g = (int64_t)tile * kTileCols + lane;  // lane-strided columns: g, g+32, g+64, g+96
+  float kl[4] = {0.f, 0.f, 0.f, 0.f}, ll[4] = {0.f, 0.f, 0.f, 0.f};
+  const int64_t row_begin = (int64_t)chunk * a.rows_per_cta;
+  const int64_t row_end = min(row_begin + (int64_t)a.rows_per_cta, a.Nc);
+  const int64_t plane = a.Nc * a.ld;
+  const uint32_t stream0 = brie_stream_word(BRIE_PHASE_EVAL, (uint32_t)a.model_id[m], 0u);
+  const float inv_n = 1.0f / ((float)a.n_eval * (float)a.S);
+  for (int j = 0; j < 4; ++j) {
+    const int64_t gj = g + 32 * j;
+    if (gj >= a.Ng) continue;
+    float L1 = 1.f, L2 = 1.f, L3 = 0.f;
+    if (a.eff) { L1 = a.eff[gj]; L2 = a.eff[a.ld + gj]; L3 = a.eff[2 * a.ld + gj]; }
+    const float lL1 = logf(L1), lL2 = logf(L2), lL3 = a.eff ? logf(L3) : 0.f;
+    float b = 0.f, tau = 0.f;
+    if (!a.cell_mode) { b = a.b[(int64_t)m * a.ld + gj]; tau = a.tau[(int64_t)m * a.ld + gj]; }
+    for (int64_t row = row_begin + warp; row < row_end; row += kWarps) {
+      const int64_t off = row * a.ld + gj;
+      const float mu = a.Zl[(int64_t)m * plane + off], lam = a.Zs[(int64_t)m * plane + off];
+      if (a.cell_mode) { b = a.b[(int64_t)m * a.Nc + row]; tau = a.tau[(int64_t)m * a.Nc + row]; }
+      float pm = b;
+      for (int k = 0; k < a.KC; ++k)
+        pm = fmaf(a.Xc[row * a.KC + k], a.Wc[((int64_t)m * a.KC + k) * a.ld + gj], pm);
+      for (int k = 0; k < a.KG; ++k)
+        pm = fmaf(a.Wg[((int64_t)m * a.Nc + row) * a.KG + k], a.Xg[gj * a.KG + k], pm);
+      const float d = lam - tau;
+      const float r0 = (mu - pm) * expf(-tau);
+      kl[j] += 0.5f * r0 * r0 + 0.5f * expm1f(2.0f * d) - d;
+      const float c1 = a.c[0][off], c2 = a.c[1][off], c3 = a.c[2] ? a.c[2][off] : 0.f;
+      const float n = c1 + c2 + c3;
+      if (n > 0.f) {
+        const float s = expf(lam);
+        float acc = 0.f;
+        for (int it = 0; it < a.n_eval; ++it) {
+          for (int s0 = 0; s0 < a.S; s0 += 4) {
+            float eps[4];
+            brie_normals4((uint32_t)(a.event_offset + gj), (uint32_t)row, (uint32_t)it,
+                          stream0 + (uint32_t)(s0 >> 2), a.seed, eps);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              if (s0 + q < a.S) {
+                const float z = fmaf(s, eps[q], mu);
+                const float e = expf(-fabsf(z));
+                const float lsp = fminf(z, 0.f) - log1pf(e);
+                const float inv = 1.0f / (1.0f + e);
+                const float psi = z >= 0.f ? inv : e * inv;
+                const float qq = z >= 0.f ? e * inv : inv;
+                const float D = fmaf(psi, L1, fmaf(qq, L2, L3));
+                acc += fmaf(c1, lsp, c2 * (lsp - z)) - (a.eff ? n * logf(D) : 0.f);
+              }
+            }
+          }
+        }
+        ll[j] += fmaf(acc, inv_n, fmaf(c1, lL1, fmaf(c2, lL2, c3 * lL3)));
+      }
+    }
+  }
+  __shared__ float red[kWarps][kTileCols];
+  for (int i = 0; i < 2; ++i) {
+    for (int j = 0; j < 4; ++j) red[warp][lane + 32 * j] = i == 0 ? kl[j] : ll[j];
+    __syncthreads();
+    const int64_t gcol = (int64_t)tile * kTileCols + threadIdx.x;
+    if (threadIdx.x < kTileCols && gcol < a.ld) {
+      float s = 0.f;
+      for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
+      a.part_ev[(((int64_t)chunk * a.M + m) * 2 + i) * a.ld + gcol] = s;
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) eval_reduce_kernel(const float* part_ev, int n_chunks, int M,
+                                                          int64_t ld, int64_t Ng, float* out) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (g >= ld) return;
+  double kl = 0.0, ll = 0.0;
+  if (g < Ng) {
+    for (int c = 0; c < n_chunks; ++c) {
+      kl += (double)part_ev[(((int64_t)c * M + m) * 2 + 0) * ld + g];
+      ll += (double)part_ev[(((int64_t)c * M + m) * 2 + 1) * ld + g];
+    }
+  }
+  out[(int64_t)m * ld + g] = (float)(kl - ll);
+}
+
+// Psi = sigmoid(Z_loc); Psi95CI = sigmoid(Z_loc + z975 s) - sigmoid(Z_loc - z975 s)
+// (tfd.LogitNormal(...).quantile, model_TFProb.py:92-106); Z_std = exp(Z_std_log).
+__device__ __forceinline__ float sigmoid_acc(float z) {
+  const float e = expf(-fabsf(z));
+  const float inv = 1.0f / (1.0f + e);
+  return z >= 0.f ? inv : e * inv;
+}
+
+__global__ void __launch_bounds__(256) posterior_kernel(const float* Zl, const float* Zs, int64_t n,
+                                                        float* Psi, float* CI, float* Zstd) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const float mu = Zl[i], s = expf(Zs[i]);
+    if (Psi) Psi[i] = sigmoid_acc(mu);
+    if (CI) CI[i] = sigmoid_acc(fmaf(kZ975, s, mu)) - sigmoid_acc(fmaf(-kZ975, s, mu));
+    if (Zstd) Zstd[i] = s;
+  }
+}
+
+// out[s, r, c] = normal s of counter (col_offset + c, row_offset + r, step, stream).
+__global__ void __launch_bounds__(256) normals_kernel(uint64_t seed, uint32_t phase, uint32_t model,
+                                                      uint32_t step, int n_samples, int64_t n_rows,
+                                                      int64_t n_cols, int64_t col_offset,
+                                                      int64_t row_offset, int64_t ld_out, float* out) {
+  const int64_t total = n_rows * n_cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n_cols, c = i % n_cols;
+    for (int s0 = 0; s0 < n_samples; s0 += 4) {
+      float e[4];
+      brie_normals4((uint32_t)(col_offset + c), (uint32_t)(row_offset + r), step,
+                    brie_stream_word(phase, model, (uint32_t)(s0 >> 2)), seed, e);
+      for (int q = 0; q < 4 && s0 + q < n_samples; ++q)
+        out[((int64_t)(s0 + q) * n_rows + r) * ld_out + c] = e[q];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(float* p, int64_t n, float v) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+// Sum the per-event loss trace over reference batches (global event groups).
+__global__ void __launch_bounds__(128) group_trace_kernel(const float* trace, int trace_cap,
+                                                          int64_t ld, int64_t Ng,
+                                                          int64_t event_offset, int64_t group_size,
+                                                          int64_t first_group, int64_t n_groups,
+                                                          int n_slots, double* out) {
+  const int slot = blockIdx.x, m = blockIdx.y;
+  const float* row = trace + ((int64_t)m * trace_cap + slot) * ld;
+  for (int64_t grp = threadIdx.x; grp < n_groups; grp += blockDim.x) {
+    const int64_t lo = max((first_group + grp) * group_size - event_offset, (int64_t)0);
+    const int64_t hi = min((first_group + grp + 1) * group_size - event_offset, Ng);
+    double s = 0.0;
+    for (int64_t g = lo; g < hi; ++g) s += (double)row[g];
+    out[((int64_t)m * n_groups + grp) * n_slots + slot] = s;
+  }
+}
+
+}  // namespace brie

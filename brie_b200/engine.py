@@ -1,0 +1,328 @@
+"""Batched BRIE2 fit engine: the thin Python layer over the C ABI.
+
+One `FitEngine` holds the device state of M models (the base/full model and the
+LRT refits of brie/models/model_wrap.py:155-187) over one event shard on one GPU
+and drives the reference's optimisation schedule (brie/models/model_TFProb.py:
+214-273) with every (model, reference-batch) pair converging independently, as
+the reference's sequential per-batch fits do (model_wrap.py:241-260).
+
+torch is used for device memory, streams and (optionally) torch.distributed --
+all arithmetic on the path happens in libbrie_b200.so.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LEARNING_RATES = [0.001, 0.005, 0.01, 0.02, 0.01, 0.005]   # model_TFProb.py:234
+KC_SUPPORTED = (0, 1, 2, 4, 8)
+KG_SUPPORTED = (0, 4, 8)
+
+
+def _pad_to(k, allowed, what):
+    for a in allowed:
+        if k <= a:
+            return a
+    raise ValueError("brie_b200: %s = %d exceeds the supported maximum %d" % (what, k, allowed[-1]))
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class FitEngine:
+    """Device-resident batched fit.
+
+    Parameters
+    ----------
+    counts : list of 2 or 3 (Nc, Ng) float32 arrays (numpy or torch, host or device),
+        pseudo-count already applied.
+    effLen : (Ng, 6) array or None -- columns 0, 4, 5 are used (model_TFProb.py:176).
+    Xc : (Nc, Kc) cell covariates (all columns any batched model uses).
+    Xg : (Ng, Kg) gene features.
+    masks : list (one per model) of the Xc column indices that model uses.
+    model_ids : RNG model word per model (default 0..M-1).
+    intercept, sigma : None (trainable) or constants (model_TFProb.py:67-78).
+    group_size : events per reference batch, ceil(batch_size / Nc) (model_wrap.py:242);
+        None = one group (un-batched branch, model_wrap.py:261-269).
+    event_offset : global index of this shard's first event.
+    dist_group : torch.distributed process group for event-sharded fits with shared
+        per-cell parameters (Kg > 0 or intercept_mode 'cell'); None = single GPU.
+    """
+
+    def __init__(self, counts, effLen=None, Xc=None, Xg=None, masks=None, model_ids=None,
+                 intercept=None, intercept_mode='gene', sigma=None, MC_size=1, seed=0,
+                 group_size=None, event_offset=0, n_events_total=None, device=None,
+                 trace_cap=None, dist_group=None):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("brie_b200: no CUDA device (there is no CPU fallback)")
+        self.device = torch.device(device if device is not None else "cuda")
+        Nc, Ng = counts[0].shape
+        self.Nc, self.Ng = int(Nc), int(Ng)
+        self.ld = _round_up(self.Ng, 32)
+        self.event_offset = int(event_offset)
+        self.n_events_total = int(n_events_total) if n_events_total is not None else self.event_offset + self.Ng
+        self.n_layers = len(counts)
+        self.cell_mode = intercept_mode.upper() == 'CELL'
+        self.intercept_const, self.sigma_const = intercept, sigma
+        self.S = int(MC_size)
+        self.seed = int(seed)
+        self.dist_group = dist_group
+        Xc = np.zeros((Nc, 0), np.float32) if Xc is None else np.asarray(Xc, np.float32)
+        Xg = np.zeros((Ng, 0), np.float32) if Xg is None else np.asarray(Xg, np.float32)
+        self.Kc_real, self.Kg_real = Xc.shape[1], Xg.shape[1]
+        self.Kc = _pad_to(self.Kc_real, KC_SUPPORTED, "Kc")
+        self.Kg = _pad_to(self.Kg_real, KG_SUPPORTED, "Kg")
+        if masks is None:
+            masks = [list(range(self.Kc_real))]
+        self.masks = [[int(k) for k in mk] for mk in masks]   # ordered: compact Wc row kk <-> column masks[m][kk]
+        self.M = len(self.masks)
+        self.model_ids = list(range(self.M)) if model_ids is None else [int(i) for i in model_ids]
+        self.shared = self.cell_mode or self.Kg_real > 0       # parameters shared across events
+        if group_size is None or self.shared:
+            group_size = max(self.n_events_total, 1)
+        self.group_size = int(group_size)
+        self.first_group = self.event_offset // self.group_size
+        last_group = (self.event_offset + self.Ng - 1) // self.group_size
+        self.n_groups = last_group - self.first_group + 1
+        self.trace_cap = int(trace_cap) if trace_cap is not None else 1024
+
+        dev, f32 = self.device, torch.float32
+        ld = self.ld
+
+        def padded(x):
+            t = torch.zeros((self.Nc, ld), dtype=f32, device=dev)
+            src = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
+            t[:, :self.Ng].copy_(src, non_blocking=True)
+            return t
+
+        self.counts = [padded(c) for c in counts]
+        self.h2d_bytes = sum(int(np.prod(c.shape)) * 4 for c in counts)
+        if effLen is not None:
+            eff = np.ones((3, ld), np.float32)
+            eff[:, :self.Ng] = np.asarray(effLen, np.float32)[:, [0, 4, 5]].T
+            self.eff = torch.from_numpy(eff).to(dev)
+        else:
+            self.eff = None
+        xc = np.zeros((self.Nc, max(self.Kc, 1)), np.float32)
+        xc[:, :self.Kc_real] = Xc
+        xg = np.zeros((self.Ng, max(self.Kg, 1)), np.float32)
+        xg[:, :self.Kg_real] = Xg
+        self.Xc_host, self.Xg_host = Xc, Xg
+        self.Xc = torch.from_numpy(xc[:, :max(self.Kc, 1)]).contiguous().to(dev)
+        self.Xg = torch.from_numpy(xg[:, :max(self.Kg, 1)]).contiguous().to(dev)
+
+        M = self.M
+        self.Z_loc = torch.zeros((M, self.Nc, ld), dtype=f32, device=dev)
+        self.Z_std_log = torch.zeros((M, self.Nc, ld), dtype=f32, device=dev)
+        self.adam_Z = torch.zeros((4, M, self.Nc, ld), dtype=f32, device=dev)
+        self.Wc = torch.zeros((M, max(self.Kc, 1), ld), dtype=f32, device=dev)
+        nsmall = self.Nc if self.cell_mode else ld
+        self.intercept = torch.zeros((M, nsmall), dtype=f32, device=dev)
+        self.sigma_log = torch.zeros((M, nsmall), dtype=f32, device=dev)
+        self.Wg = torch.zeros((M, self.Nc, max(self.Kg, 1)), dtype=f32, device=dev)
+        self.active = torch.zeros((M, ld), dtype=torch.uint8, device=dev)
+        self.active[:, :self.Ng] = 1
+        self.loss_trace = torch.zeros((M, self.trace_cap, ld), dtype=f32, device=dev)
+
+        d = _lib.FitDesc()
+        d.n_cells, d.n_events, d.ld, d.event_offset = self.Nc, self.Ng, ld, self.event_offset
+        d.seed = self.seed
+        d.n_models, d.Kc, d.Kg, d.mc_size = M, self.Kc, self.Kg, self.S
+        d.n_layers, d.has_efflen, d.cell_mode = self.n_layers, int(effLen is not None), int(self.cell_mode)
+        d.train_intercept, d.train_sigma = int(intercept is None), int(sigma is None)
+        d.trace_cap = self.trace_cap
+        for m in range(M):
+            d.model_id[m] = self.model_ids[m]
+            d.xc_mask[m] = sum(1 << k for k in self.masks[m])
+        self.desc = d
+        h = C.c_void_p()
+        _lib.check(self.lib.brie_fit_create(C.byref(d), C.byref(h)))
+        self.h = h
+        sz = _lib.FitSizes()
+        _lib.check(self.lib.brie_fit_get_sizes(h, C.byref(sz)))
+        self.sizes = sz
+        self.scratch = torch.zeros(int(sz.scratch_bytes // 4) + 4, dtype=f32, device=dev)
+        self.adam_small = torch.zeros(max(int(sz.adam_small_floats), 4), dtype=f32, device=dev)
+        b = _lib.FitBuffers()
+        for i in range(3):
+            b.counts[i] = self.counts[i].data_ptr() if i < self.n_layers else None
+        b.efflen3 = self.eff.data_ptr() if self.eff is not None else None
+        b.Xc, b.Xg = self.Xc.data_ptr(), self.Xg.data_ptr()
+        b.Z_loc, b.Z_std_log, b.adam_Z = self.Z_loc.data_ptr(), self.Z_std_log.data_ptr(), self.adam_Z.data_ptr()
+        b.Wc, b.intercept, b.sigma_log = self.Wc.data_ptr(), self.intercept.data_ptr(), self.sigma_log.data_ptr()
+        b.Wg, b.adam_small = self.Wg.data_ptr(), self.adam_small.data_ptr()
+        b.active, b.loss_trace, b.scratch = self.active.data_ptr(), self.loss_trace.data_ptr(), self.scratch.data_ptr()
+        self.bufs = b
+        _lib.check(self.lib.brie_fit_bind(h, C.byref(b)))
+        self.n_iter = None
+        self.losses = None
+        self.loss_gene = None
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h is not None and h.value:
+            self.lib.brie_fit_destroy(h)
+            self.h = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def launch_count(self):
+        return int(self.lib.brie_fit_launch_count(self.h))
+
+    def init_params(self, init_objs=None):
+        """Model_init (model_TFProb.py:12-31): counter-based random init on the device,
+        or injected per-model init objects with attributes intercept, sigma, Z_loc,
+        Z_std (or Z_std_log), Wc_loc (compact rows), Wg_loc -- the reference's
+        `init_obj` hook (model_TFProb.py:45, 62-65)."""
+        with torch.cuda.device(self.device):
+            ic = 0.0 if self.intercept_const is None else float(self.intercept_const)
+            sc = 1.0 if self.sigma_const is None else float(self.sigma_const)
+            _lib.check(self.lib.brie_fit_init_params(self.h, ic, sc, self._stream()))
+            for m, mk in enumerate(self.masks):
+                # the ABI fills compact rows in ascending column order; a refit that APPENDS its
+                # tested column (model_wrap.py:167) has that column as its last compact row
+                if mk != sorted(mk):
+                    self.Wc[m, mk] = self.Wc[m, sorted(mk)].clone()
+            if init_objs is None:
+                return
+            for m, ob in enumerate(init_objs):
+                if ob is None:
+                    continue
+                f = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
+                self.Z_loc[m, :, :self.Ng] = f(ob.Z_loc)
+                if hasattr(ob, 'Z_std_log'):
+                    self.Z_std_log[m, :, :self.Ng] = f(ob.Z_std_log)
+                else:
+                    self.Z_std_log[m, :, :self.Ng] = f(np.log(np.asarray(ob.Z_std, np.float32)))
+                wc = np.asarray(ob.Wc_loc, np.float32).reshape(len(self.masks[m]), self.Ng)
+                for kk, k in enumerate(self.masks[m]):
+                    self.Wc[m, k, :self.Ng] = f(wc[kk])
+                if self.Kg_real > 0:
+                    self.Wg[m, :, :self.Kg_real] = f(np.asarray(ob.Wg_loc).reshape(self.Nc, self.Kg_real))
+                    self.Wg[m, :, self.Kg_real:] = 0
+                n = self.Nc if self.cell_mode else self.Ng
+                self.intercept[m, :n] = f(np.asarray(ob.intercept, np.float32).reshape(-1))
+                self.sigma_log[m, :n] = f(np.log(np.asarray(ob.sigma, np.float32).reshape(-1)))
+
+    def begin_stage(self, lr):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.brie_fit_begin_stage(self.h, float(lr), self._stream()))
+
+    def run_steps(self, n, trace_slot0=-1):
+        with torch.cuda.device(self.device):
+            if self.dist_group is None or not self.shared:
+                _lib.check(self.lib.brie_fit_run_steps(self.h, int(n), int(trace_slot0), self._stream()))
+                return
+            import torch.distributed as dist
+            p, nf = C.c_void_p(), C.c_int64()
+            _lib.check(self.lib.brie_fit_cell_grad(self.h, C.byref(p), C.byref(nf)))
+            off = (p.value - self.scratch.data_ptr()) // 4
+            G = self.scratch[off:off + nf.value]
+            for i in range(n):
+                slot = trace_slot0 + i if trace_slot0 >= 0 else -1
+                _lib.check(self.lib.brie_fit_step_phase(self.h, 0, slot, self._stream()))
+                dist.all_reduce(G, group=self.dist_group)   # NCCL: shared-weight gradients only
+                _lib.check(self.lib.brie_fit_step_phase(self.h, 1, slot, self._stream()))
+
+    def group_trace(self, n_slots):
+        """(M, n_groups, n_slots) float64 sums of the per-event loss trace per reference batch."""
+        out = torch.zeros((self.M, self.n_groups, n_slots), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.brie_fit_group_trace(self.h, int(n_slots), self.group_size, self.n_groups,
+                                                     out.data_ptr(), self._stream()))
+        if self.dist_group is not None and self.shared:
+            import torch.distributed as dist
+            dist.all_reduce(out, group=self.dist_group)
+        return out.cpu().numpy()
+
+    def set_active_groups(self, act):
+        """act: (M, n_groups) bool -> per-event active mask."""
+        g = (np.arange(self.Ng) + self.event_offset) // self.group_size - self.first_group
+        ev = np.zeros((self.M, self.ld), np.uint8)
+        ev[:, :self.Ng] = act[:, g]
+        self.active.copy_(torch.from_numpy(ev).to(self.device))
+
+    def eval_loss_gene(self, n_eval=500):
+        out = torch.zeros((self.M, self.ld), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.brie_fit_eval_loss_gene(self.h, int(n_eval), out.data_ptr(), self._stream()))
+        return out[:, :self.Ng]
+
+    def posterior(self, model=0):
+        """Psi, Psi95CI, Z_std (model_TFProb.py:88-106) as device tensors (Nc, Ng) views."""
+        outs = [torch.empty((self.Nc, self.ld), dtype=torch.float32, device=self.device) for _ in range(3)]
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.brie_fit_posterior(self.h, int(model), outs[0].data_ptr(), outs[1].data_ptr(),
+                                                   outs[2].data_ptr(), self._stream()))
+        return [o[:, :self.Ng] for o in outs]
+
+    # ------------------------------------------------------------------ schedule
+    def fit(self, min_iter=1000, max_iter=5000, add_iter=500, epsilon_conv=1e-2, n_eval=500,
+            init_objs=None, do_init=True):
+        """BRIE2.fit (model_TFProb.py:214-273) for all batched models at once."""
+        n_stage = int(min_iter / 6)
+        if max(n_stage, add_iter) > self.trace_cap:
+            raise ValueError("trace_cap %d too small for %d-step stages" % (self.trace_cap, max(n_stage, add_iter)))
+        if do_init:
+            self.init_params(init_objs)
+        M, NG = self.M, self.n_groups
+        for i, lr in enumerate(LEARNING_RATES):                      # :234-241
+            self.begin_stage(lr)
+            self.run_steps(n_stage, 0 if i == len(LEARNING_RATES) - 1 else -1)
+        if n_stage > 0:
+            tr = self.group_trace(n_stage).astype(np.float32)        # (M, NG, n_stage)
+        else:
+            tr = np.zeros((M, NG, 0), np.float32)
+        traces = [[tr[m, g] for g in range(NG)] for m in range(M)]
+        n_iter = np.full((M, NG), min_iter, np.int64)                # :247
+        d1 = int(min(50, add_iter / 2))
+        d2 = d1 * 2
+        active = np.ones((M, NG), bool)
+        while True:                                                  # :250-258
+            for m in range(M):
+                for g in range(NG):
+                    if active[m, g]:
+                        L = traces[m][g]
+                        with np.errstate(invalid='ignore'):
+                            cond = (L[-d2:-d1].mean() - L[-d1:].mean() > epsilon_conv) if L.size else False
+                        active[m, g] = bool(cond) and n_iter[m, g] < max_iter
+            if not active.any():
+                break
+            self.set_active_groups(active)
+            self.run_steps(add_iter, 0)
+            tr = self.group_trace(add_iter).astype(np.float32)
+            for m in range(M):
+                for g in range(NG):
+                    if active[m, g]:
+                        traces[m][g] = np.concatenate([traces[m][g], tr[m, g]])
+                        n_iter[m, g] += add_iter
+        self.set_active_groups(np.ones((M, NG), bool))
+        self.n_iter = n_iter
+        self.traces = traces
+        # BRIE_RV.concate appends the per-batch traces end to end (model_wrap.py:61)
+        self.losses = [np.concatenate(traces[m]) if NG else np.zeros(0, np.float32) for m in range(M)]
+        self.loss_gene = self.eval_loss_gene(n_eval)                 # :261-264
+        return self.losses
+
+    # ------------------------------------------------------------------ results
+    def model_params(self, m):
+        """Host copies in the reference's shapes for model m."""
+        Ng = self.Ng
+        out = {}
+        out['Wc_loc'] = self.Wc[m, self.masks[m], :Ng].cpu().numpy() if self.masks[m] \
+            else np.zeros((0, Ng), np.float32)
+        out['Wg_loc'] = self.Wg[m, :, :self.Kg_real].cpu().numpy()
+        if self.cell_mode:
+            out['intercept'] = self.intercept[m, :self.Nc].cpu().numpy().reshape(self.Nc, 1)
+            out['sigma'] = np.exp(self.sigma_log[m, :self.Nc].cpu().numpy()).reshape(self.Nc, 1)
+        else:
+            out['intercept'] = self.intercept[m, :Ng].cpu().numpy().reshape(1, Ng)
+            out['sigma'] = np.exp(self.sigma_log[m, :Ng].cpu().numpy()).reshape(1, Ng)
+        return out

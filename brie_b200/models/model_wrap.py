@@ -1,0 +1,325 @@
+"""Wrap functions for running BRIE2 -- drop-in for brie/models/model_wrap.py.
+
+`fit_BRIE_matrix` and `fitBRIE` keep the reference's signatures, defaults, prints
+and outputs (brie/models/model_wrap.py:88-199, 202-314).  What changes is the
+execution plan: the base/full fit and every LRT refit (the Python loop at
+model_wrap.py:156-187) run as one batched `FitEngine`, and the sequential event
+batches of `fitBRIE` (model_wrap.py:241-260) become convergence groups inside
+the same launches, so one pass over the counts serves all of them.
+"""
+import numpy as np
+from scipy.stats import chi2
+
+from ..engine import FitEngine
+from ..settings import verbosity
+
+
+def fdr_bh(pvals):
+    """Benjamini-Hochberg adjusted p-values, as statsmodels
+    `multipletests(p, method="fdr_bh")[1]` used at model_wrap.py:195."""
+    p = np.asarray(pvals, float)
+    n = p.size
+    if n == 0:
+        return p.copy()
+    order = np.argsort(p)
+    adj = p[order] * n / np.arange(1, n + 1)
+    adj = np.minimum.accumulate(adj[::-1])[::-1]
+    adj[adj > 1] = 1
+    out = np.empty(n)
+    out[order] = adj
+    return out
+
+
+class BRIE_RV():
+    """Return value object for BRIE2 model (model_wrap.py:15-76)."""
+
+    def __init__(self, model=None):
+        if model is None:
+            return
+        self.Nc, self.Ng, self.Kc, self.Kg = model.Nc, model.Ng, model.Kc, model.Kg
+        self.shape = (self.Nc, self.Ng)
+        self.Xc, self.Xg = model.Xc, model.Xg
+        self.sigma = model.sigma.numpy()
+        self.intercept = model.intercept.numpy()
+        self.cell_coeff = model.Wc_loc.numpy()
+        self.gene_coeff = model.Wg_loc.numpy()
+        self.Psi = model.Psi.numpy()
+        self.Psi95CI = model.Psi95CI
+        self.Z_loc = model.Z_loc.numpy()
+        self.Z_std = model.Z_std.numpy()
+        self.losses = model.losses.numpy()
+        self.loss_gene = model.loss_gene.numpy()
+        self.intercept_mode = model.intercept_mode
+
+    @property
+    def Wc_loc(self):
+        return self.cell_coeff
+
+    @property
+    def Wg_loc(self):
+        return self.gene_coeff
+
+    def __str__(self):
+        return "BRIE2 results for %d cells and %d genes" % (self.Nc, self.Ng)
+
+    def concate(self, new_RV, axis=1):
+        if axis != 1:
+            print("Warning: only suppoting gene level concate!")
+            return None
+        self.Ng += new_RV.Ng
+        self.shape = (self.Nc, self.Ng)
+        self.losses = np.append(self.losses, new_RV.losses)
+        self.loss_gene = np.append(self.loss_gene, new_RV.loss_gene)
+        self.sigma = np.append(self.sigma, new_RV.sigma, axis=1)
+        self.intercept = np.append(self.intercept, new_RV.intercept, axis=1)
+        self.cell_coeff = np.append(self.cell_coeff, new_RV.cell_coeff, axis=1)
+        self.Psi = np.append(self.Psi, new_RV.Psi, axis=1)
+        self.Psi95CI = np.append(self.Psi95CI, new_RV.Psi95CI, axis=1)
+        self.Z_std = np.append(self.Z_std, new_RV.Z_std, axis=1)
+        self.Z_loc = np.append(self.Z_loc, new_RV.Z_loc, axis=1)
+        if hasattr(new_RV, 'ELBO_gain'):
+            self.fdr = np.append(self.fdr, new_RV.fdr, axis=0)
+            self.pval = np.append(self.pval, new_RV.pval, axis=0)
+            self.ELBO_gain = np.append(self.ELBO_gain, new_RV.ELBO_gain, axis=0)
+        if hasattr(new_RV, 'n_iter'):
+            self.n_iter = np.append(self.n_iter, new_RV.n_iter, axis=1)
+
+
+def concate(BRIE_RV_list):
+    """Concate a list of BRIE results (model_wrap.py:78-85)."""
+    res_merge = BRIE_RV_list[0]
+    for _res in BRIE_RV_list[1:]:
+        res_merge.concate(_res)
+    return res_merge
+
+
+def _rv_from_engine(eng, m, Xc_model, Xg, intercept_mode):
+    rv = BRIE_RV()
+    rv.Nc, rv.Ng = eng.Nc, eng.Ng
+    rv.Kc, rv.Kg = len(eng.masks[m]), eng.Kg_real
+    rv.shape = (rv.Nc, rv.Ng)
+    rv.Xc, rv.Xg = Xc_model, Xg
+    p = eng.model_params(m)
+    rv.sigma, rv.intercept = p['sigma'], p['intercept']
+    rv.cell_coeff, rv.gene_coeff = p['Wc_loc'], p['Wg_loc']
+    Psi, CI, Zstd = eng.posterior(m)
+    rv.Psi, rv.Psi95CI, rv.Z_std = Psi.cpu().numpy(), CI.cpu().numpy(), Zstd.cpu().numpy()
+    rv.Z_loc = eng.Z_loc[m, :, :eng.Ng].cpu().numpy()
+    rv.losses = eng.losses[m]
+    rv.loss_gene = eng.loss_gene[m].cpu().numpy()
+    rv.intercept_mode = intercept_mode
+    return rv
+
+
+def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
+                    intercept_mode='gene', LRT_index=None, pseudo_count=0.01,
+                    sigma=None, base_mode='full', tau_prior=[3, 27], **keyargs):
+    """Fit a BRIE model with cell and/or gene features (model_wrap.py:88-199).
+
+    Extra keyword arguments consumed here (not in the reference): `seed` (noise and
+    init key, default 0), `group_size` / `event_offset` / `n_events_total` (reference
+    batch geometry when called from fitBRIE), `device`, `init_objs` (per-model
+    injected initial values: [base, refit_0, ...]), `n_eval` (loss_gene evaluations,
+    500 in the reference), `dist_group`.  All other **keyargs go to the fit schedule
+    as in the reference (`min_iter, max_iter, add_iter, epsilon_conv, MC_size`).
+    """
+    from scipy.sparse import issparse
+    seed = keyargs.pop('seed', 0)
+    group_size = keyargs.pop('group_size', None)
+    event_offset = keyargs.pop('event_offset', 0)
+    n_events_total = keyargs.pop('n_events_total', None)
+    device = keyargs.pop('device', None)
+    init_objs = keyargs.pop('init_objs', None)
+    dist_group = keyargs.pop('dist_group', None)
+    n_eval = keyargs.pop('n_eval', 500)
+    MC_size = keyargs.pop('MC_size', 1)
+    for k in ('target', 'optimizer', 'learn_rate', 'verbose'):      # accepted and ignored (:214-237)
+        keyargs.pop(k, None)
+
+    for i in range(len(data)):                                      # :108-111
+        if issparse(data[i]):
+            data[i] = data[i].toarray().astype(np.float32)
+
+    print("[BRIE2] adding pseudo_count:", pseudo_count)             # :113-117 (in place, like the reference)
+    idx = data[0] + data[1] > 0
+    for i in range(2):
+        data[i][idx] = data[i][idx] + pseudo_count
+
+    Nc, Ng = data[0].shape
+    if Xc is None:
+        Xc = np.ones((Nc, 0), np.float32)
+    if Xg is None:
+        Xg = np.ones((Ng, 0), np.float32)
+    Xc = np.asarray(Xc, np.float32)
+    Xg = np.asarray(Xg, np.float32)
+    Kc = Xc.shape[1]
+
+    full = base_mode.upper() == 'FULL'
+    if full:                                                        # :130-136
+        base_cols = list(range(Kc))
+    elif LRT_index is not None and len(LRT_index) < Kc:
+        base_cols = [k for k in range(Kc) if k not in set(int(i) for i in LRT_index)]
+    else:
+        base_cols = []
+    if LRT_index is None:                                           # :149-150
+        LRT_index = np.arange(Kc)
+    LRT_index = [int(i) for i in LRT_index]
+
+    # column masks over the full Xc: model 0 = base/full, model 1+ii = refit ii (:156-171)
+    test_masks = []
+    for idx_k in LRT_index:
+        if full:
+            if verbosity == 3:
+                print("[BRIE2] fitting null model without feature %d" % (idx_k))
+            test_masks.append([k for k in range(Kc) if k != idx_k])
+        else:
+            if verbosity == 3:
+                print("[BRIE2] fitting test model by add feature %d" % (idx_k))
+            test_masks.append(base_cols + [idx_k])
+
+    trace_cap = max(int(keyargs.get('min_iter', 1000) / 6), int(keyargs.get('add_iter', 500)), 1)
+    common = dict(effLen=effLen, Xc=Xc, Xg=Xg, intercept=intercept, sigma=sigma, MC_size=MC_size,
+                  seed=seed, group_size=group_size, event_offset=event_offset,
+                  n_events_total=n_events_total, device=device, trace_cap=trace_cap,
+                  dist_group=dist_group)
+    cell_mode = intercept_mode.upper() == 'CELL'
+    T = len(test_masks)
+    # NB the reference builds the refits WITHOUT intercept_mode (model_wrap.py:174-178), so
+    # they always use the default per-event ('gene') intercept/sigma layout.
+    if cell_mode and T > 0:
+        engines = [FitEngine(data, masks=[base_cols], model_ids=[0], intercept_mode=intercept_mode, **common),
+                   FitEngine(data, masks=test_masks, model_ids=list(range(1, T + 1)), intercept_mode='gene',
+                             **common)]
+        where = [(0, 0)] + [(1, i) for i in range(T)]
+        inits = [None if init_objs is None else init_objs[:1], None if init_objs is None else init_objs[1:]]
+    else:
+        engines = [FitEngine(data, masks=[base_cols] + test_masks, model_ids=list(range(T + 1)),
+                             intercept_mode=intercept_mode, **common)]
+        where = [(0, i) for i in range(T + 1)]
+        inits = [init_objs]
+    for eng, io in zip(engines, inits):
+        eng.fit(n_eval=n_eval, init_objs=io, **keyargs)             # :144, :180
+
+    e0, m0 = engines[where[0][0]], where[0][1]
+    brie_results = _rv_from_engine(e0, m0, Xc[:, base_cols], Xg, intercept_mode)   # :146
+    brie_results.n_iter = np.stack([engines[w[0]].n_iter[w[1]] for w in where], axis=0)  # (1+T, groups)
+    brie_results.launch_count = sum(e.launch_count for e in engines)
+    brie_results.h2d_bytes = sum(e.h2d_bytes for e in engines)
+    if T == 0:                                                      # :152-153
+        return brie_results
+
+    ELBO_gain = np.zeros((Ng, T), dtype=np.float32)                 # :155
+    for ii, idx_k in enumerate(LRT_index):
+        et, mt = engines[where[1 + ii][0]], where[1 + ii][1]
+        lg_test = et.loss_gene[mt].cpu().numpy()
+        if full:
+            ELBO_gain[:, ii] = lg_test - brie_results.loss_gene     # :183
+        else:
+            ELBO_gain[:, ii] = brie_results.loss_gene - lg_test     # :185
+            wc_last = et.Wc[mt, idx_k, :Ng].cpu().numpy()[None, :]
+            brie_results.cell_coeff = np.append(brie_results.cell_coeff, wc_last, axis=0)  # :186-187
+    brie_results.ELBO_gain = ELBO_gain                              # H1 vs NUll
+    brie_results.pval = chi2.sf(2 * ELBO_gain, df=1)                # :190
+    fdr = np.zeros(ELBO_gain.shape)
+    for i in range(fdr.shape[1]):
+        fdr[:, i] = fdr_bh(brie_results.pval[:, i])                 # :193-196
+    brie_results.fdr = fdr
+    return brie_results
+
+
+def _device_event_budget(Nc, n_models, n_layers, device=None, frac=0.7):
+    """Events per device chunk so that counts + (1+T) model states + outputs fit in HBM."""
+    import torch
+    free, _ = torch.cuda.mem_get_info(device)
+    per_event = Nc * 4 * (n_layers + 6 * n_models + 3 + 1) * 1.05
+    return max(int(free * frac / per_event), 1)
+
+
+def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
+            LRT_index=[], layer_keys=['isoform1', 'isoform2', 'ambiguous'],
+            batch_size=500000, pseudo_count=0.01, sigma=None,
+            base_mode='full', tau_prior=[3, 27], **keyargs):
+    """Fit a BRIE model from AnnData with cell and/or gene features (model_wrap.py:202-314).
+
+    Returns the BRIE_RV result and adds to `adata` exactly the keys the reference adds
+    (obsm['Xc'], varm['cell_coeff'], varm['Xg'], obsm['gene_coeff'], varm|obsm['intercept',
+    'sigma'], layers['Psi','Z_std','Psi_95CI'], uns['brie_losses'], var['loss_gene'],
+    varm['fdr','pval','ELBO_gain'], uns['brie_param']).
+    """
+    if Xc is None:
+        Xc = np.ones((adata.shape[0], 0), np.float32)
+    if Xg is None:
+        Xg = np.ones((adata.shape[1], 0), np.float32)
+    if LRT_index is None:
+        LRT_index = np.arange(Xc.shape[1])
+    Nc, Ng = adata.shape
+    n_models = 1 + len(LRT_index)
+
+    if (Xg is None or Xg.shape[1] == 0) and intercept_mode.upper() != 'CELL':   # :241
+        # Events are independent here; the reference fits them in sequential batches of
+        # _n_gene events (:242-258).  We keep _n_gene as the convergence group and fit as many
+        # groups per launch as HBM holds.
+        _n_gene = int(np.ceil(batch_size / Nc))
+        chunk = _device_event_budget(Nc, n_models, len(layer_keys), keyargs.get('device'))
+        chunk = max(chunk // _n_gene, 1) * _n_gene
+        res_list = []
+        for e0 in range(0, Ng, chunk):
+            _idx = range(e0, min(e0 + chunk, Ng))
+            _count_layers = [adata.layers[_key][:, _idx] for _key in layer_keys]
+            _effLen = adata.varm['effLen'][_idx, :] if 'effLen' in adata.varm else None
+            _ResVal = fit_BRIE_matrix(
+                _count_layers, Xc=Xc, Xg=Xg[_idx, :], effLen=_effLen,
+                intercept=intercept, intercept_mode=intercept_mode,
+                LRT_index=LRT_index, pseudo_count=pseudo_count, sigma=sigma,
+                base_mode=base_mode, tau_prior=tau_prior, group_size=_n_gene,
+                event_offset=e0, n_events_total=Ng, **keyargs)
+            res_list.append(_ResVal)
+            print("[BRIE2] %d out %d genes done" % (min(e0 + chunk, Ng), Ng))
+        ResVal = concate(res_list)
+    else:                                                           # :261-269
+        _count_layers = [adata.layers[_key] for _key in layer_keys]
+        _effLen = adata.varm['effLen'] if 'effLen' in adata.varm else None
+        ResVal = fit_BRIE_matrix(
+            _count_layers, Xc=Xc, Xg=Xg, effLen=_effLen, intercept=intercept,
+            intercept_mode=intercept_mode, LRT_index=LRT_index,
+            pseudo_count=pseudo_count, sigma=sigma, base_mode=base_mode,
+            tau_prior=tau_prior, **keyargs)
+
+    # update adata (:271-311)
+    if Xc.shape[0] > 0:
+        adata.obsm['Xc'] = Xc
+        adata.varm['cell_coeff'] = ResVal.cell_coeff.T
+    if Xg.shape[1] > 0:
+        adata.varm['Xg'] = Xg
+        adata.obsm['gene_coeff'] = ResVal.gene_coeff
+    if ResVal.intercept_mode == 'gene':
+        adata.varm['intercept'] = ResVal.intercept.T
+        adata.varm['sigma'] = ResVal.sigma.T
+    elif ResVal.intercept_mode == 'cell':
+        adata.obsm['intercept'] = ResVal.intercept
+        adata.obsm['sigma'] = ResVal.sigma
+    else:
+        adata.varm['sigma'] = ResVal.sigma.T
+
+    adata.layers['Psi'] = ResVal.Psi
+    adata.layers['Z_std'] = ResVal.Z_std
+    adata.layers['Psi_95CI'] = ResVal.Psi95CI
+
+    adata.uns['brie_losses'] = ResVal.losses
+    adata.var['loss_gene'] = ResVal.loss_gene
+
+    if LRT_index is None or len(LRT_index) >= 1:
+        adata.varm['fdr'] = ResVal.fdr
+        adata.varm['pval'] = ResVal.pval
+        adata.varm['ELBO_gain'] = ResVal.ELBO_gain
+
+    adata.uns['brie_param'] = {
+        'LRT_index': LRT_index,
+        'base_mode': base_mode,
+        'intecept': intercept,
+        'intercept_mode': intercept_mode,
+        'sigma': sigma,
+        'pseudo_count': pseudo_count,
+        'layer_keys': layer_keys
+    }
+    return ResVal

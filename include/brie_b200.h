@@ -1,0 +1,168 @@
+/* brie_b200 C ABI -- the drop-in boundary under the reference's Python object protocol.
+ *
+ * The reference (huangyh09/brie v2.3.0) has no FFI: `fit_BRIE_matrix`
+ * (brie/models/model_wrap.py:138-146, 174-187) talks to `BRIE2`
+ * (brie/models/model_TFProb.py:35-273) through Python attributes.  This ABI is
+ * what a `BRIE2`-compatible class binds with ctypes instead of TensorFlow; each
+ * entry names the reference code it replaces.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *  - All array pointers are DEVICE pointers unless the name ends in `_host`.
+ *  - Every (cells, events) matrix is row-major with leading dimension `ld`
+ *    floats (ld % 4 == 0, ld >= n_events); columns >= n_events are padding and
+ *    must hold zero counts.  Same layout as the reference's (Nc, Ng) tensors.
+ *  - `n_models` independent models (the full/base fit plus the LRT refits of
+ *    model_wrap.py:155-187) are batched in every launch; model-major arrays are
+ *    (n_models, ...).  A refit "without covariate k" is the same design matrix
+ *    with bit k cleared in `xc_mask[model]` (its Wc row stays 0).
+ *  - The caller owns every buffer; the library allocates no persistent device
+ *    memory.  Handles own small host structs only.
+ *  - Every function returns 0 on success, <0 on error; brie_last_error() gives
+ *    the message (thread-local).  No exceptions cross the ABI.
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it,
+ *    nothing synchronises unless documented.
+ */
+#ifndef BRIE_B200_H
+#define BRIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRIE_ABI_VERSION 1
+#define BRIE_MAX_MODELS 32
+#define BRIE_MAX_KC 8
+#define BRIE_MAX_KG 8
+
+#define BRIE_OK 0
+#define BRIE_ERR_ARG (-1)
+#define BRIE_ERR_CUDA (-2)
+#define BRIE_ERR_UNSUPPORTED (-3)
+
+typedef struct brie_fit_desc {
+  int64_t n_cells;        /* Nc  (model_TFProb.py:46) */
+  int64_t n_events;       /* Ng of this shard (model_TFProb.py:47) */
+  int64_t ld;             /* leading dimension of (cells, events) arrays */
+  int64_t event_offset;   /* global index of local event 0 (RNG counters) */
+  uint64_t seed;          /* noise / init key */
+  int32_t n_models;       /* 1 + number of LRT refits batched (model_wrap.py:156) */
+  int32_t Kc;             /* columns of Xc, 0..BRIE_MAX_KC (model_TFProb.py:48) */
+  int32_t Kg;             /* columns of Xg, 0..BRIE_MAX_KG (model_TFProb.py:49) */
+  int32_t mc_size;        /* MC_size (model_TFProb.py:130) */
+  int32_t n_layers;       /* 2 or 3 count layers (model_TFProb.py:184) */
+  int32_t has_efflen;     /* 0: binomial branch :162-167; 1: effLen branch :168-185 */
+  int32_t cell_mode;      /* 0: intercept/sigma (1,Ng); 1: (Nc,1) (model_TFProb.py:53-60) */
+  int32_t train_intercept;/* intercept is a Variable (model_TFProb.py:67-71) */
+  int32_t train_sigma;    /* sigma_log is a Variable (model_TFProb.py:73-78) */
+  int32_t trace_cap;      /* slots in loss_trace per model */
+  int32_t model_id[BRIE_MAX_MODELS]; /* RNG model word of each batched model */
+  uint32_t xc_mask[BRIE_MAX_MODELS]; /* bit k set: model uses Xc column k */
+} brie_fit_desc;
+
+typedef struct brie_fit_sizes {
+  size_t scratch_bytes;     /* brie_fit_buffers.scratch */
+  size_t adam_small_floats; /* brie_fit_buffers.adam_small */
+  int32_t rows_per_cta;
+  int32_t n_row_chunks;
+  int32_t n_col_tiles;
+  int32_t reserved;
+} brie_fit_sizes;
+
+typedef struct brie_fit_buffers {
+  const float* counts[3]; /* (Nc, ld) isoform1, isoform2, ambiguous (NULL if n_layers == 2),
+                             pseudo-count already applied (model_wrap.py:113-117) */
+  const float* efflen3;   /* (3, ld): columns 0, 4, 5 of varm['effLen'] (model_TFProb.py:176); NULL if !has_efflen */
+  const float* Xc;        /* (Nc, Kc) row-major (model_TFProb.py:220) */
+  const float* Xg;        /* (Ng, Kg) row-major (model_TFProb.py:221) */
+  float* Z_loc;           /* (M, Nc, ld)  (model_TFProb.py:80) */
+  float* Z_std_log;       /* (M, Nc, ld)  (model_TFProb.py:82) */
+  float* adam_Z;          /* (4, M, Nc, ld): m(Z_loc), v(Z_loc), m(Z_std_log), v(Z_std_log) */
+  float* Wc;              /* (M, Kc, ld)  (model_TFProb.py:84) */
+  float* intercept;       /* (M, ld) or, cell_mode, (M, Nc)  (model_TFProb.py:68) */
+  float* sigma_log;       /* same shape as intercept (model_TFProb.py:74) */
+  float* Wg;              /* (M, Nc, Kg)  (model_TFProb.py:85) */
+  float* adam_small;      /* Adam moments of Wc, intercept, sigma_log, Wg */
+  const uint8_t* active;  /* (M, ld): 1 = this model still optimises this event */
+  float* loss_trace;      /* (M, trace_cap, ld): per-step per-event loss (pre-update) */
+  void* scratch;
+} brie_fit_buffers;
+
+typedef struct brie_fit brie_fit; /* opaque */
+
+int brie_abi_version(void);
+const char* brie_last_error(void);
+
+/* Replaces BRIE2.__init__ bookkeeping (model_TFProb.py:42-85): validates the
+ * description, picks the launch geometry and reports scratch sizes. */
+int brie_fit_create(const brie_fit_desc* desc, brie_fit** out);
+int brie_fit_destroy(brie_fit* fit);
+int brie_fit_get_sizes(const brie_fit* fit, brie_fit_sizes* out);
+int brie_fit_bind(brie_fit* fit, const brie_fit_buffers* buffers);
+
+/* Replaces Model_init (model_TFProb.py:12-31): Z_loc ~ N(0,1), Z_std_log ~ N(0,1),
+ * Wc ~ N(0,1) on unmasked rows (compact row index as if masked rows were deleted),
+ * Wg ~ N(0,1), intercept ~ N(0,1) if trained else `intercept_const`,
+ * sigma_log = log(sigma_const) (1 -> 0).  Counter-based, see brie_philox.h. */
+int brie_fit_init_params(brie_fit* fit, float intercept_const, float sigma_const, void* stream);
+
+/* Replaces `tf.optimizers.Adam(learning_rate=lr)` (model_TFProb.py:237): zero
+ * all Adam moments and reset the step count t of every model. */
+int brie_fit_begin_stage(brie_fit* fit, float lr, void* stream);
+
+/* Replaces `tfp.math.minimize(loss_fn, num_steps, optimizer)` (model_TFProb.py:239,
+ * 255): n_steps fused ELBO forward + backward + Adam steps (get_loss :194-211,
+ * logLik_MC :130-191, Z_prior :118-127, constraint clips :68-69, :80-81).
+ * If trace_slot0 >= 0 the pre-update per-event loss of step i is written to
+ * loss_trace[:, trace_slot0 + i, :]; if < 0 the loss is not evaluated. */
+int brie_fit_run_steps(brie_fit* fit, int32_t n_steps, int32_t trace_slot0, void* stream);
+
+/* All-reduce hook for event-sharded fits with shared per-cell parameters
+ * (Kg > 0 or cell_mode).  brie_fit_run_steps_split runs ONE step in two halves:
+ * phase 0 leaves the summed per-cell gradients in cell_grad (M, Nc, n_cell_acc)
+ * (pointer returned by brie_fit_cell_grad) for the caller to all-reduce; phase 1
+ * applies Adam to Wg / per-cell intercept / sigma_log. */
+int brie_fit_step_phase(brie_fit* fit, int32_t phase, int32_t trace_slot, void* stream);
+int brie_fit_cell_grad(brie_fit* fit, float** ptr, int64_t* n_floats);
+
+/* Replaces the 500x `get_loss(axis=0)` averaging (model_TFProb.py:261-264):
+ * loss_gene[m, g] = sum_c KL - mean over n_eval*S fresh-noise samples of sum_c loglik. */
+int brie_fit_eval_loss_gene(brie_fit* fit, int32_t n_eval, float* loss_gene /* (M, ld) */, void* stream);
+
+/* Replaces the Psi / Psi95CI / Z_std properties (model_TFProb.py:88-106) for one model. */
+int brie_fit_posterior(brie_fit* fit, int32_t model, float* Psi, float* Psi95CI, float* Z_std,
+                       void* stream);
+
+/* Sum the per-event loss trace over reference batches (model_wrap.py:241-246:
+ * group g covers events [g*group_size, (g+1)*group_size) in GLOBAL event index):
+ * out[m, grp, slot] for slot in [0, n_slots).  Feeds the convergence rule of
+ * model_TFProb.py:250-251 and uns['brie_losses']. */
+int brie_fit_group_trace(brie_fit* fit, int32_t n_slots, int64_t group_size, int64_t n_groups,
+                         double* out /* (M, n_groups, n_slots) */, void* stream);
+
+/* Total kernels launched by this handle so far (bench.py's gpu_launches). */
+int64_t brie_fit_launch_count(const brie_fit* fit);
+
+/* Noise dumps (tests): eps[s, r, c] for rows [0,n_rows), global cols col_offset + [0,n_cols). */
+int brie_philox_normals_host(uint64_t seed, uint32_t phase, uint32_t model, uint32_t step,
+                             int32_t n_samples, int64_t n_rows, int64_t n_cols, int64_t col_offset,
+                             float* out_host);
+int brie_philox_normals_device(uint64_t seed, uint32_t phase, uint32_t model, uint32_t step,
+                               int32_t n_samples, int64_t n_rows, int64_t n_cols, int64_t col_offset,
+                               float* out, void* stream);
+
+/* Synthetic counts on the device, following brie/models/simulator.py:54-73 and
+ * simulator/simuPSI.py:129-130 (bench.py workloads too large for host RAM).
+ * psi (Nc, ld) in; per-event L (3, ld), rate lam (ld), detection prob cdr (ld). */
+int brie_simulate_counts(uint64_t seed, int64_t n_cells, int64_t n_events, int64_t ld,
+                         int64_t event_offset, const float* logit_mean /* (ld) */,
+                         const float* logit_sd /* (ld) */, const float* Xc, const float* Wc,
+                         int32_t Kc, const float* efflen3, const float* lam, const float* cdr,
+                         float pseudo_count, float* c1, float* c2, float* c3, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BRIE_B200_H */

@@ -1,0 +1,201 @@
+"""GPU parity: CUDA path (through the C ABI) vs the CPU oracle on the same seeded
+inputs, same injected initial values and the same injected MC noise.
+
+Tolerances (BASELINE.json north_star): ELBO within 1e-4 relative, Psi posterior
+means within 1e-3 absolute, LRT statistics (ELBO_gain) within 1e-3 relative,
+DAS calls at FDR 0.05 identical.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import philox_np as px
+from oracle.brie2_oracle import OracleBRIE2, OracleInit, add_pseudo_count, oracle_fit_matrix
+
+from util import device_eps_provider, make_problem
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _engine(data, eff, Xc, Xg, **kw):
+    from brie_b200.engine import FitEngine
+    return FitEngine(data, effLen=eff, Xc=Xc, Xg=Xg, **kw)
+
+
+def test_device_normals_match_numpy_spec():
+    from brie_b200 import _lib
+    lib = _lib.load()
+    for (phase, model, step, S, R, Cn, off) in [(0, 0, 0, 3, 17, 33, 0), (1, 5, 77, 5, 4, 9, 1000),
+                                                (2, 3, 1, 1, 8, 130, 12345)]:
+        out = torch.empty((S, R, Cn), dtype=torch.float32, device="cuda")
+        _lib.check(lib.brie_philox_normals_device(99, phase, model, step, S, R, Cn, off, out.data_ptr(), None))
+        torch.cuda.synchronize()
+        ref = px.normal_field(R, Cn, step, phase, model, 99, S, col_offset=off)
+        assert np.abs(out.cpu().numpy() - ref).max() < 2e-5
+        host = np.empty((S, R, Cn), np.float32)
+        _lib.check(lib.brie_philox_normals_host(99, phase, model, step, S, R, Cn, off, host.ctypes.data))
+        assert np.abs(host - ref).max() < 2e-6
+
+
+CASES = [
+    # mode, effLen, n_layers, Kc, Kg, intercept, sigma
+    ('gene', True, 3, 0, 0, None, None),
+    ('gene', True, 3, 1, 0, None, None),
+    ('gene', True, 2, 2, 0, None, None),
+    ('gene', False, 2, 1, 0, None, None),
+    ('None', True, 3, 3, 0, 0, None),        # CLI default: intercept fixed at 0 (quant.py:205)
+    ('gene', True, 3, 1, 3, None, None),     # gene features
+    ('cell', False, 2, 1, 2, None, None),    # DMG-style: per-cell intercept + gene features
+    ('cell', True, 3, 0, 0, None, 2.0),      # fixed sigma
+]
+
+
+@pytest.mark.parametrize("mode,eff,n_layers,Kc,Kg,intercept,sigma", CASES)
+def test_first_step_loss_and_gradients(mode, eff, n_layers, Kc, Kg, intercept, sigma):
+    """One fused step: the per-event loss trace equals the oracle's loss_gene and the Adam
+    first moments equal 0.1 * gradient for every trainable variable."""
+    Nc, Ng, S, seed = 150, 203, 3, 11
+    data, effLen, Xc, Xg = make_problem(Nc, Ng, Kc, Kg, eff, n_layers)
+    add_pseudo_count(data, np.float32(0.01))
+    eng = _engine(data, effLen, Xc, Xg, intercept=intercept, intercept_mode=mode, sigma=sigma, MC_size=S,
+                  seed=seed, trace_cap=8)
+    eng.init_params()
+    om = OracleBRIE2(Nc, Ng, Kc, Kg, effLen, intercept, mode, sigma, dtype=np.float64, seed=seed)
+    # device init == oracle init (same counters)
+    assert np.abs(eng.Z_loc[0, :, :Ng].cpu().numpy() - om.p['Z_loc']).max() < 2e-5
+    assert np.abs(eng.Z_std_log[0, :, :Ng].cpu().numpy() - om.p['Z_std_log']).max() < 2e-5
+    pr = eng.model_params(0)
+    assert np.abs(pr['Wc_loc'] - om.p['Wc_loc']).max(initial=0) < 2e-5
+    assert np.abs(pr['Wg_loc'] - om.p['Wg_loc']).max(initial=0) < 2e-5
+    assert np.abs(pr['intercept'] - om.p['intercept']).max() < 2e-5
+    # feed the oracle the device's exact values
+    om.p['Z_loc'] = eng.Z_loc[0, :, :Ng].cpu().numpy().astype(np.float64)
+    om.p['Z_std_log'] = eng.Z_std_log[0, :, :Ng].cpu().numpy().astype(np.float64)
+    om.p['Wc_loc'] = pr['Wc_loc'].astype(np.float64)
+    om.p['Wg_loc'] = pr['Wg_loc'].astype(np.float64)
+    om.p['intercept'] = pr['intercept'].astype(np.float64)
+    om.Xc, om.Xg = Xc.astype(np.float64), Xg.astype(np.float64)
+    eps = device_eps_provider(seed, 0, Nc, Ng)(px.PHASE_TRAIN, 0, S)
+    loss, loss_gene, grads = om.loss_and_grads(data, eps)
+
+    eng.begin_stage(0.001)
+    eng.run_steps(1, 0)
+    torch.cuda.synchronize()
+    tr = eng.loss_trace[0, 0, :Ng].cpu().numpy()
+    assert np.abs(tr - loss_gene).max() <= 1e-4 * np.abs(loss_gene).max()
+    assert abs(tr.sum() - loss) <= 1e-5 * abs(loss)
+
+    def close(dev, ref, name):
+        scale = max(np.abs(ref).max(), 1.0)
+        assert np.abs(dev - ref).max() <= 2e-4 * scale, name
+
+    close(10 * eng.adam_Z[0, 0, :, :Ng].cpu().numpy(), grads['Z_loc'], 'Z_loc')
+    close(10 * eng.adam_Z[2, 0, :, :Ng].cpu().numpy(), grads['Z_std_log'], 'Z_std_log')
+    ld, KC, KGp = eng.ld, eng.Kc, eng.Kg
+    small = eng.adam_small.cpu().numpy()
+    ev = small[:2 * (KC + 2) * ld].reshape(2, KC + 2, ld)[0]
+    cellp = small[2 * (KC + 2) * ld:2 * (KC + 2) * ld + 2 * Nc * (KGp + 2)].reshape(2, Nc, KGp + 2)[0]
+    if Kc > 0:
+        close(10 * ev[:Kc, :Ng], grads['Wc_loc'], 'Wc')
+    cellm = mode.upper() == 'CELL'
+    if 'intercept' in grads:
+        close(10 * (cellp[:, KGp] if cellm else ev[KC, :Ng]), grads['intercept'].reshape(-1), 'intercept')
+    if 'sigma_log' in grads:
+        close(10 * (cellp[:, KGp + 1] if cellm else ev[KC + 1, :Ng]), grads['sigma_log'].reshape(-1), 'sigma_log')
+    if Kg > 0:
+        close(10 * cellp[:, :Kg], grads['Wg_loc'], 'Wg')
+
+
+@pytest.mark.parametrize("mode,eff,n_layers,Kc,Kg,intercept,sigma", [CASES[1], CASES[4], CASES[6]])
+def test_trajectory_parity(mode, eff, n_layers, Kc, Kg, intercept, sigma):
+    """60 optimisation steps (2 Adam stages) track the float32 oracle step for step."""
+    Nc, Ng, S, seed = 96, 131, 3, 5
+    data, effLen, Xc, Xg = make_problem(Nc, Ng, Kc, Kg, eff, n_layers, seed=3)
+    add_pseudo_count(data, np.float32(0.01))
+    eng = _engine(data, effLen, Xc, Xg, intercept=intercept, intercept_mode=mode, sigma=sigma, MC_size=S,
+                  seed=seed, trace_cap=64)
+    eng.init_params()
+    om = OracleBRIE2(Nc, Ng, Kc, Kg, effLen, intercept, mode, sigma, dtype=np.float64, seed=seed)
+    om.Xc, om.Xg = Xc.astype(np.float64), Xg.astype(np.float64)
+    from oracle.brie2_oracle import _Adam
+    names = om.trainable()
+    epsf = device_eps_provider(seed, 0, Nc, Ng)
+    step = 0
+    for lr in (0.01, 0.02):
+        eng.begin_stage(lr)
+        eng.run_steps(30, 0)
+        adam = _Adam(lr, {k: om.p[k] for k in names}, np.float64)
+        ref_losses = []
+        for _ in range(30):
+            loss, _, grads = om.loss_and_grads(data, epsf(px.PHASE_TRAIN, step, S))
+            ref_losses.append(loss)
+            adam.apply(om.p, {k: grads[k] for k in names})
+            np.clip(om.p['Z_loc'], -9, 9, out=om.p['Z_loc'])
+            if om.train_intercept:
+                np.clip(om.p['intercept'], -9, 9, out=om.p['intercept'])
+            step += 1
+        tr = eng.group_trace(30)[0, 0]
+        assert np.abs(tr - np.array(ref_losses)).max() <= 1e-4 * np.abs(ref_losses).max()
+    assert np.abs(eng.Z_loc[0, :, :Ng].cpu().numpy() - om.p['Z_loc']).max() < 2e-3
+    assert np.abs(eng.Z_std_log[0, :, :Ng].cpu().numpy() - om.p['Z_std_log']).max() < 2e-3
+    pr = eng.model_params(0)
+    assert np.abs(pr['Wc_loc'] - om.p['Wc_loc']).max(initial=0) < 2e-3
+    assert np.abs(pr['sigma'] - om.sigma).max() < 2e-3
+
+
+def test_loss_gene_eval_parity():
+    Nc, Ng, S, seed, n_eval = 64, 77, 3, 2, 12
+    data, effLen, Xc, Xg = make_problem(Nc, Ng, 1, 0, True, 3, seed=4)
+    add_pseudo_count(data, np.float32(0.01))
+    eng = _engine(data, effLen, Xc, None, MC_size=S, seed=seed, trace_cap=8)
+    eng.init_params()
+    lg = eng.eval_loss_gene(n_eval)[0].cpu().numpy()
+    om = OracleBRIE2(Nc, Ng, 1, 0, effLen, None, 'gene', None, dtype=np.float64, seed=seed)
+    om.Xc = Xc.astype(np.float64)
+    epsf = device_eps_provider(seed, 0, Nc, Ng)
+    ref = np.zeros(Ng)
+    for it in range(n_eval):
+        ref += om.loss_and_grads(data, epsf(px.PHASE_EVAL, it, S), want_grads=False)[1]
+    ref /= n_eval
+    assert np.abs(lg - ref).max() <= 2e-5 * np.abs(ref).max()
+
+
+def test_full_fit_with_lrt_matches_oracle():
+    """fit_BRIE_matrix end to end (schedule, convergence extension, loss_gene, LRT, FDR)
+    against oracle_fit_matrix with the same noise."""
+    from brie_b200.models import fit_BRIE_matrix
+    Nc, Ng, seed = 120, 48, 21
+    data, effLen, Xc, _ = make_problem(Nc, Ng, 1, 0, True, 3, seed=8)
+    # plant a strong effect of the covariate on a third of the events
+    rng = np.random.default_rng(0)
+    kw = dict(min_iter=600, max_iter=1600, add_iter=500, MC_size=3, n_eval=40)
+    res = fit_BRIE_matrix([x.copy() for x in data], Xc=Xc, effLen=effLen, intercept=None, intercept_mode='gene',
+                          LRT_index=None, seed=seed, **kw)
+
+    class Prov:
+        def __init__(self):
+            self.cache = {}
+
+    def provider_for(model_id):
+        return device_eps_provider(seed, model_id, Nc, Ng)
+
+    # oracle with the device's noise: patch OracleBRIE2.eps per model id
+    import oracle.brie2_oracle as ob
+    orig = ob.OracleBRIE2.eps
+    ob.OracleBRIE2.eps = lambda self, phase, step, S: provider_for(self.model_id)(phase, step, S)
+    try:
+        ref = oracle_fit_matrix([x.copy() for x in data], Xc=Xc, effLen=effLen, intercept=None,
+                                intercept_mode='gene', LRT_index=None, dtype=np.float32, seed=seed, **kw)
+    finally:
+        ob.OracleBRIE2.eps = orig
+    assert list(res.n_iter[:, 0]) == list(ref.n_iter)
+    assert np.abs(res.Psi - ref.Psi).max() < 1e-3
+    assert np.abs(res.loss_gene - ref.loss_gene).max() <= 1e-4 * np.abs(ref.loss_gene).max()
+    assert abs(res.losses[-1] - ref.losses[-1]) <= 1e-4 * abs(ref.losses[-1])
+    big = np.abs(ref.ELBO_gain) > 0.5
+    assert np.abs(res.ELBO_gain - ref.ELBO_gain)[big].max(initial=0) <= 1e-3 * np.abs(ref.ELBO_gain)[big].max(initial=1)
+    assert np.abs(res.ELBO_gain - ref.ELBO_gain).max() < 5e-3
+    assert ((res.fdr < 0.05) == (ref.fdr < 0.05)).all()
