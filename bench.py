@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- BRIE2 VI-fit hot path on B200.
+
+Metric (BASELINE.json): cell x event x MC-sample ELBO fwd+bwd per second.
+Workload at N=1: BASELINE config C2 "Smart-seq2-scale DAS": 5 000 cells x 5 000
+events, 1 cell covariate + LRT (full + 1 null model batched, M = 2), 3 count layers
+with effective lengths, MC_size 3, --interceptMode gene.  One "step" = one fused
+ELBO forward+backward+Adam step of both models over the whole 5k x 5k batch.
+At N>1 every rank runs its own C2-sized event shard (events are independent, no
+data-path collective): weak scaling.
+
+  value  : device-resident throughput, CUDA events around K steps, max over ranks
+  e2e    : the same metric through the public API `fit_BRIE_matrix` with HOST
+           numpy inputs: H2D of the counts, the full default brie-quant schedule
+           (--minIter 5000 --maxIter 20000 --MCsize 3, batchSize 500000 groups),
+           500-sample loss_gene, LRT, D2H of Psi / Psi_95CI / Z_std
+  roofline: fused step kernel, algorithmic bytes (12 + 48 M per cell-event-step)
+           / CUDA-event kernel time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline: the restated reference (oracle/brie2_torch_eager.py, op-for-op
+           PyTorch-CPU eager, not TensorFlow) on one reference batch
+           (5 000 cells x 100 events) on the box's host cores.
+
+`--impl reference` times that restated reference alone (the real reference needs
+TensorFlow, which cannot be installed here).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NC, NG, S, KC, M = 5000, 5000, 3, 1, 2
+METRIC = "cell x event x MC-sample ELBO fwd+bwd per second"
+UNIT = "cell*event*sample/s"
+WORKLOAD = ("C2 Smart-seq2-scale DAS: 5000 cells x 5000 events, 3 count layers + effLen, Kc=1, "
+            "LRT full+null batched (M=2), MC_size=3, interceptMode gene")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0, period_ms=100):
+        self.lines, self.proc = [], None
+        self.index, self.period = index, period_ms
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-i", str(self.index),
+                 "-lms", str(self.period)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(self.period / 1000.0 * 1.5)
+        self.proc.terminate()
+        rows = [l for (t, l) in self.lines if (t0 is None or t >= t0) and (t1 is None or t <= t1 + 0.15)]
+        if len(rows) < 3:
+            rows = [l for (_, l) in self.lines]
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[2])); smax.append(float(f[3])); power.append(float(f[4]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v == "Active":
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_c2(seed):
+    from brie_b200.utils.synth import simulate_counts
+    d = simulate_counts(NC, NG, design='binary1', seed=seed, with_efflen=True, n_layers=3)
+    return d['layers'], d['effLen'], d['Xc']
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_run(n_steps, warmup, threads, n_events=100, seed=1):
+    """Restated reference (op-for-op torch-CPU eager + autograd + TF-form Adam) on one
+    reference batch: 5000 cells x 100 events = --batchSize 500000 (model_wrap.py:242)."""
+    import torch
+    from oracle.brie2_torch_eager import EagerBRIE2
+    from oracle.brie2_oracle import OracleInit, add_pseudo_count
+    from brie_b200.utils.synth import simulate_counts
+    torch.set_num_threads(threads)
+    d = simulate_counts(NC, n_events, design='binary1', seed=seed)
+    data = [x.copy() for x in d['layers']]
+    add_pseudo_count(data, np.float32(0.01))
+    init = OracleInit(NC, n_events, KC, 0, (1, n_events), (1, n_events), None, None, seed=seed)
+    m = EagerBRIE2(NC, n_events, KC, 0, d['effLen'], None, 'gene', None, init, torch.float32)
+    m.set_design(d['Xc'], None)
+    cl = [torch.from_numpy(x) for x in data]
+    st = {'t': 0, 'm': {}, 'v': {}}
+    gen = torch.Generator().manual_seed(seed)
+    times = []
+    for i in range(warmup + n_steps):
+        t0 = time.perf_counter()
+        eps = torch.randn((S, NC, n_events), generator=gen)      # tfd.Normal.sample cost is part of the step
+        m.train_step(cl, eps, st, 0.01)
+        times.append(time.perf_counter() - t0)
+    dt = float(np.sum(times[warmup:]))
+    return NC * n_events * S * n_steps / dt, dt / n_steps * 1e3, "%d cells x %d events (one --batchSize 500000 reference batch), %d steps, S=%d" % (
+        NC, n_events, n_steps, S)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    steps = max(args.steps, 1)
+    n = min(steps, 60)
+    val, ms, sample = cpu_reference_run(n, min(args.warmup, 3), threads)
+    out = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+           "steps": n, "warmup": min(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": WORKLOAD, "note": "restated reference (PyTorch-CPU eager, not TensorFlow: TF/TFP "
+                      "are not installable here); one step = fwd+bwd+Adam of ONE model over a bounded sample: " + sample},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-min-iter", type=int, default=5000)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    from brie_b200.engine import FitEngine
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    W = max(args.warmup, 3)
+    K = max(args.steps, 1)
+
+    layers, effLen, Xc = make_c2(seed=1 + rank)
+    idx = layers[0] + layers[1] > 0                         # pseudo-count, model_wrap.py:113-117
+    for i in range(2):
+        layers[i][idx] += np.float32(0.01)
+    nnz_frac = float(np.mean(layers[0] + layers[1] + layers[2] > 0))
+
+    eng = FitEngine(layers, effLen=effLen, Xc=Xc, masks=[[0], []], model_ids=[0, 1], intercept=None,
+                    intercept_mode='gene', sigma=None, MC_size=S, seed=7, group_size=100,
+                    event_offset=rank * NG, n_events_total=world * NG, trace_cap=8,
+                    device="cuda:%d" % local)
+    eng.init_params()
+    eng.begin_stage(0.01)
+    eng.run_steps(W)
+    torch.cuda.synchronize()
+    eng.kernel_timing(K)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    e0.record()
+    eng.run_steps(K)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = eng.launch_count - l0
+    kms, kn = eng.kernel_time_ms()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    units_per_step = NC * NG * S * M
+    value = world * units_per_step * K / (ms * 1e-3)
+
+    # roofline of the fused step kernel: algorithmic bytes = 12 B counts (shared by the M models)
+    # + 48 B state per model per cell x event
+    peak, peak_src = hbm_peak()
+    alg_bytes = NC * NG * (12 + 48 * M)
+    k_ms = kms / max(kn, 1)
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": "elbo_step_kernel<KC=1,KG=0,gene,noloss>", "achieved": achieved, "peak": peak,
+            "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "kernel_ms": k_ms, "kernel_share_of_step": kms / ms if world == 1 else None,
+            "algorithmic_bytes_per_launch": alg_bytes}
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        roof["traffic"] = json.load(open(tp)).get("dram_bytes_per_launch")
+
+    del eng
+    torch.cuda.empty_cache()
+
+    e2e = None
+    fit_wall = None
+    if not args.no_e2e:
+        # public API with host buffers; every rank fits its own shard, time = max over ranks
+        from brie_b200.models import fit_BRIE_matrix
+        layers2, effLen2, Xc2 = make_c2(seed=1 + rank)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = fit_BRIE_matrix(layers2, Xc=Xc2, effLen=effLen2, intercept=None, intercept_mode='gene',
+                                  LRT_index=None, min_iter=args.e2e_min_iter, max_iter=4 * args.e2e_min_iter,
+                                  MC_size=S, group_size=100, event_offset=rank * NG, n_events_total=world * NG,
+                                  seed=7)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        n_stage = int(args.e2e_min_iter / 6)
+        ran = (res.n_iter - args.e2e_min_iter) + 6 * n_stage          # steps actually run per (model, group)
+        units = float(ran.sum()) * NC * 100 * S
+        steps_max = int(ran.max())
+        d2h = 4 * NC * NG * 4 + 3 * NG * 4
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        fit_wall = dt
+        e2e = {"value": world * units / dt, "unit": UNIT, "h2d_bytes_per_step": res.h2d_bytes / steps_max,
+               "d2h_bytes_per_step": d2h / steps_max, "wall_s": dt, "steps_max": steps_max,
+               "min_iter": args.e2e_min_iter, "max_iter": 4 * args.e2e_min_iter,
+               "api": "brie_b200.models.fit_BRIE_matrix(host numpy) -> full schedule + loss_gene + LRT + D2H",
+               "fdr05_calls": int((res.fdr < 0.05).sum()), "launches": int(res.launch_count)}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        v, cms, sample = cpu_reference_run(40, 3, threads)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "ms_per_step": cms,
+               "note": "restated reference, PyTorch-CPU eager -- not TensorFlow"}
+
+    if rank == 0:
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+               "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "f32", "data": "synthetic",
+               "config": {"workload": WORKLOAD, "cells": NC, "events_per_gpu": NG, "models": M, "mc_size": S,
+                          "nonzero_fraction": nnz_frac, "l2": "state 2.7 GB per GPU >> 126 MB L2 (inputs larger than L2)",
+                          "parallelism": "events sharded x%d, no collective" % world},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+               "cpu_baseline": cpu, "fit_lrt_wall_s": fit_wall}
+        print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

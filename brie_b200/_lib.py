@@ -9,7 +9,7 @@ import os
 
 BRIE_MAX_MODELS = 32
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbrie_b200.so")
+LIB_PATH = os.environ.get("BRIE_LIB_PATH", os.path.join(_HERE, "libbrie_b200.so"))
 
 
 class FitDesc(C.Structure):
@@ -61,6 +61,8 @@ SYMBOLS = {
     "brie_fit_posterior": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
     "brie_fit_group_trace": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "brie_fit_launch_count": (C.c_int64, [_P]),
+    "brie_fit_kernel_timing": (C.c_int, [_P, C.c_int32]),
+    "brie_fit_kernel_time_ms": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "brie_philox_normals_host": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32,
                                            C.c_int64, C.c_int64, C.c_int64, _P]),
     "brie_philox_normals_device": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32,

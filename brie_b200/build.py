@@ -24,7 +24,9 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", OUT]
+    extra = os.environ.get("BRIE_NVCC_EXTRA", "").split()
+    out = os.environ.get("BRIE_LIB_OUT", OUT)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", out]
     subprocess.run(cmd, check=True)
     return OUT
 

@@ -9,6 +9,7 @@
 
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/brie_b200.h"
 #include "brie_kernels.cuh"
@@ -52,6 +53,9 @@ struct brie_fit {
   float alpha = 0.f;
   int64_t launches = 0;
   bool step_open = false;    // phase 0 done, phase 1 pending
+  // optional CUDA-event timing of the fused step kernel (bench.py roofline)
+  std::vector<cudaEvent_t> ev0, ev1;
+  int ev_used = 0;
 };
 
 using namespace brie;
@@ -179,7 +183,40 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
 }
 
 int brie_fit_destroy(brie_fit* fit) {
+  if (fit) {
+    for (cudaEvent_t e : fit->ev0) cudaEventDestroy(e);
+    for (cudaEvent_t e : fit->ev1) cudaEventDestroy(e);
+  }
   delete fit;
+  return BRIE_OK;
+}
+
+int brie_fit_kernel_timing(brie_fit* f, int32_t capacity) {
+  if (!f || capacity < 0) return fail(BRIE_ERR_ARG, "bad argument");
+  for (cudaEvent_t e : f->ev0) cudaEventDestroy(e);
+  for (cudaEvent_t e : f->ev1) cudaEventDestroy(e);
+  f->ev0.assign(capacity, nullptr);
+  f->ev1.assign(capacity, nullptr);
+  f->ev_used = 0;
+  for (int i = 0; i < capacity; ++i) {
+    BRIE_CUDA(cudaEventCreate(&f->ev0[i]));
+    BRIE_CUDA(cudaEventCreate(&f->ev1[i]));
+  }
+  return BRIE_OK;
+}
+
+int brie_fit_kernel_time_ms(brie_fit* f, double* total_ms, int32_t* n_launches) {
+  if (!f || !total_ms || !n_launches) return fail(BRIE_ERR_ARG, "null argument");
+  double sum = 0.0;
+  for (int i = 0; i < f->ev_used; ++i) {
+    BRIE_CUDA(cudaEventSynchronize(f->ev1[i]));
+    float ms = 0.f;
+    BRIE_CUDA(cudaEventElapsedTime(&ms, f->ev0[i], f->ev1[i]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *n_launches = f->ev_used;
+  f->ev_used = 0;
   return BRIE_OK;
 }
 
@@ -310,7 +347,10 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
     a.M = M; a.S = d.mc_size; a.rows_per_cta = f->sz.rows_per_cta;
     for (int m = 0; m < M; ++m) a.model_id[m] = d.model_id[m];
     const dim3 grid(M, f->sz.n_col_tiles, f->sz.n_row_chunks);
+    const bool timed = f->ev_used < (int)f->ev0.size();
+    if (timed) BRIE_CUDA(cudaEventRecord(f->ev0[f->ev_used], s));
     BRIE_CUDA(dispatch_step(a, d.Kc, d.Kg, d.cell_mode != 0, loss, grid, s));
+    if (timed) BRIE_CUDA(cudaEventRecord(f->ev1[f->ev_used++], s));
     f->launches += 1;
 
     const int nev = d.Kc + (d.cell_mode ? 0 : 2) + (loss ? 2 : 0);

@@ -176,6 +176,15 @@ class FitEngine:
     def launch_count(self):
         return int(self.lib.brie_fit_launch_count(self.h))
 
+    def kernel_timing(self, capacity):
+        _lib.check(self.lib.brie_fit_kernel_timing(self.h, int(capacity)))
+
+    def kernel_time_ms(self):
+        """(summed ms, launches) of the fused step kernel since timing was armed."""
+        ms, n = C.c_double(), C.c_int32()
+        _lib.check(self.lib.brie_fit_kernel_time_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
     def init_params(self, init_objs=None):
         """Model_init (model_TFProb.py:12-31): counter-based random init on the device,
         or injected per-model init objects with attributes intercept, sigma, Z_loc,

@@ -145,6 +145,12 @@ int brie_fit_group_trace(brie_fit* fit, int32_t n_slots, int64_t group_size, int
 /* Total kernels launched by this handle so far (bench.py's gpu_launches). */
 int64_t brie_fit_launch_count(const brie_fit* fit);
 
+/* Measurement aid (no reference counterpart): bracket the next `capacity` launches of
+ * the fused step kernel with CUDA events on the launching stream; _time_ms waits for
+ * them, returns their summed duration and count, and re-arms the same capacity. */
+int brie_fit_kernel_timing(brie_fit* fit, int32_t capacity);
+int brie_fit_kernel_time_ms(brie_fit* fit, double* total_ms, int32_t* n_launches);
+
 /* Noise dumps (tests): eps[s, r, c] for rows [0,n_rows), global cols col_offset + [0,n_cols). */
 int brie_philox_normals_host(uint64_t seed, uint32_t phase, uint32_t model, uint32_t step,
                              int32_t n_samples, int64_t n_rows, int64_t n_cols, int64_t col_offset,

@@ -116,7 +116,7 @@ class EagerBRIE2:
         loss = self.get_loss(count_layers, eps)
         gs = torch.autograd.grad(loss, list(vs.values()))
         self.adam_step(state, lr, dict(zip(vs.keys(), gs)))
-        return float(loss)
+        return float(loss.detach())
 
     def set_design(self, Xc, Xg):
         self.Xc = None if Xc is None else torch.as_tensor(np.asarray(Xc), dtype=self.dtype)
