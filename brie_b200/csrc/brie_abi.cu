@@ -67,7 +67,14 @@ bool kg_supported(int k) { return k == 0 || k == 4 || k == 8; }
 
 template <int KC, int KG, bool CELL, bool LOSS>
 cudaError_t launch_step(const StepArgs& a, dim3 grid, cudaStream_t s) {
-  elbo_step_kernel<KC, KG, CELL, LOSS><<<grid, kThreads, 0, s>>>(a);
+  static bool configured = false;  // per instantiation: opt in to > 48 KB dynamic shared memory
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(elbo_step_kernel<KC, KG, CELL, LOSS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  elbo_step_kernel<KC, KG, CELL, LOSS><<<grid, kThreads, kStepSmemBytes, s>>>(a);
   return cudaGetLastError();
 }
 

@@ -75,6 +75,35 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ float lg2_approx(float x) {
+  float y;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// exp / log on the SFU (ex2/lg2.approx.ftz): 2 ulp-class, no denormal fix-up code
+__device__ __forceinline__ float fast_exp(float x) { return ex2_approx(x * kLog2e); }
+__device__ __forceinline__ float fast_log(float x) { return lg2_approx(x) * kLn2; }
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(valid ? 16 : 0)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // keras Adam update_step (TF 2.15): m += (g-m)(1-b1); v += (g^2-v)(1-b2);
 // x -= alpha_t * m / (sqrt(v) + eps)
 __device__ __forceinline__ void adam_update(float& x, float& m, float& v, float g, float alpha) {
@@ -104,6 +133,7 @@ __device__ __forceinline__ void mc_samples(float mu, float s, float c1, float c2
                                            uint32_t stream0, uint64_t seed, float& gsum,
                                            float& gesum, float& llsum) {
   gsum = 0.f; gesum = 0.f; llsum = 0.f;
+  const float ndL = n * dL;
   for (int s0 = 0; s0 < S; s0 += 4) {
     float eps[4];
     brie_normals4(event, cell, step, stream0 + (uint32_t)(s0 >> 2), seed, eps);
@@ -111,18 +141,18 @@ __device__ __forceinline__ void mc_samples(float mu, float s, float c1, float c2
     for (int j = 0; j < 4; ++j) {
       if (s0 + j < S) {
         const float z = fmaf(s, eps[j], mu);
-        const float e = __expf(-fabsf(z));
+        const float e = ex2_approx(-kLog2e * fabsf(z));      // exp(-|z|)
         const float inv = rcp_approx(1.0f + e);
         const float lo = e * inv;
         const float psi = z >= 0.f ? inv : lo;
         const float q = z >= 0.f ? lo : inv;
         const float D = fmaf(psi, L1, fmaf(q, L2, L3));
-        const float g = fmaf(c1, q, -c2 * psi) - n * psi * q * dL * rcp_approx(D);
+        const float g = fmaf(c1, q, -c2 * psi) - ndL * (psi * q) * rcp_approx(D);
         gsum += g;
         gesum = fmaf(g, eps[j], gesum);
         if (LOSS) {
-          const float lsp = fminf(z, 0.f) - __logf(1.0f + e);  // log sigmoid(z)
-          llsum += fmaf(c1, lsp, c2 * (lsp - z)) - n * __logf(D);
+          const float lsp = fminf(z, 0.f) - fast_log(1.0f + e);  // log sigmoid(z)
+          llsum += fmaf(c1, lsp, c2 * (lsp - z)) - n * fast_log(D);
         }
       }
     }
@@ -143,15 +173,25 @@ struct StepTraits {
 // grid = (M, n_col_tiles, n_row_chunks): models fastest so the CTAs sharing a
 // count tile are co-resident and the counts are fetched from HBM once.
 //
-// Each warp iteration handles one 128-event row segment in three phases:
-//   A (dense, lane = 4 events): load state + counts, KL terms and gradients, shared-
-//     parameter accumulators; elements with reads (n > 0) are pushed, compacted by
-//     ballot/popc prefix, into the warp's shared-memory work queue;
+// Each warp walks its rows of one 128-event segment through a private two-stage
+// shared-memory ring filled with cp.async (16 B per lane per array, 9 arrays =
+// 4.6 KB per row): the next row streams in from HBM while the current one is
+// processed, so loads in flight do not depend on register-resident state.  A lane
+// reads back exactly the bytes it copied, so the ring needs no barrier.
+// One row is processed in three phases:
+//   A (dense, lane = 4 events): KL terms and gradients, shared-parameter
+//     accumulators; elements with reads (n > 0) are pushed, compacted by ballot/popc
+//     prefix, into the warp's shared-memory work queue;
 //   B (compacted): lanes take queue items round-robin and run the S Monte-Carlo
 //     samples (Philox + Box-Muller + likelihood gradient) -- zero-count elements,
 //     80-87 % of real data, cost nothing here and the lanes stay converged;
-//   C (dense): owners read their MC sums back, Adam-update and store.
-constexpr int kQueueFields = 6;  // mu, s, c1, c2, n, column  ->  results overwrite c1, c2, n
+//   C (dense): owners read their MC sums back, Adam-update and store (16 B stores).
+constexpr int kQueueFields = 6;   // mu, s, c1, c2, n, column  ->  results overwrite c1, c2, n
+constexpr int kRingArrays = 9;    // Z_loc, Z_std_log, c1, c2, c3, m_loc, v_loc, m_std, v_std
+constexpr int kRingStages = 2;
+constexpr int kStepSmemFloats =
+    kWarps * kRingStages * kRingArrays * kTileCols + kWarps * kQueueFields * kTileCols + 3 * kTileCols;
+constexpr int kStepSmemBytes = kStepSmemFloats * 4;
 
 template <int KC, int KG, bool CELL, bool LOSS>
 __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(const StepArgs a) {
@@ -170,9 +210,39 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   if (in_ld) act4 = *reinterpret_cast<const uint32_t*>(a.active + (int64_t)m * a.ld + g0);
   if (!__syncthreads_or(act4 != 0)) return;
 
-  __shared__ __align__(16) float s_queue[kWarps][kQueueFields][kTileCols];
-  __shared__ float s_L[3][kTileCols];
-  float(*q)[kTileCols] = s_queue[warp];
+  extern __shared__ __align__(128) float smem[];
+  float* s_ring = smem + warp * (kRingStages * kRingArrays * kTileCols);
+  float(*q)[kTileCols] =
+      reinterpret_cast<float(*)[kTileCols]>(smem + kWarps * kRingStages * kRingArrays * kTileCols +
+                                            warp * kQueueFields * kTileCols);
+  float(*s_L)[kTileCols] = reinterpret_cast<float(*)[kTileCols]>(
+      smem + kWarps * kRingStages * kRingArrays * kTileCols + kWarps * kQueueFields * kTileCols);
+
+  const int64_t row_begin = (int64_t)chunk * a.rows_per_cta;
+  const int64_t row_end = min(row_begin + (int64_t)a.rows_per_cta, a.Nc);
+  const int64_t plane = a.Nc * a.ld;
+  const int64_t mplane = (int64_t)a.M * plane;
+  const bool has_c3 = a.c[2] != nullptr;
+
+  // ring producer: this lane's 16-byte column of each array, one commit group per row
+  const uint32_t ring_lane = (uint32_t)__cvta_generic_to_shared(s_ring) + lane * 16;
+  auto issue_row = [&](int64_t row, int stage) {
+    const bool ok = in_ld && row < row_end;
+    const int64_t off = ok ? row * a.ld + g0 : 0;
+    const int64_t moff = ok ? (int64_t)m * plane + off : 0;
+    const uint32_t dst = ring_lane + stage * (kRingArrays * kTileCols * 4);
+    cp_async16(dst + 0 * kTileCols * 4, a.Zl + moff, ok);
+    cp_async16(dst + 1 * kTileCols * 4, a.Zs + moff, ok);
+    cp_async16(dst + 2 * kTileCols * 4, a.c[0] + off, ok);
+    cp_async16(dst + 3 * kTileCols * 4, a.c[1] + off, ok);
+    cp_async16(dst + 4 * kTileCols * 4, has_c3 ? a.c[2] + off : a.c[0], ok && has_c3);
+    cp_async16(dst + 5 * kTileCols * 4, a.aZ + moff, ok);
+    cp_async16(dst + 6 * kTileCols * 4, a.aZ + mplane + moff, ok);
+    cp_async16(dst + 7 * kTileCols * 4, a.aZ + 2 * mplane + moff, ok);
+    cp_async16(dst + 8 * kTileCols * 4, a.aZ + 3 * mplane + moff, ok);
+    cp_async_commit();
+  };
+  issue_row(row_begin + warp, 0);
 
   // per-event constants
   if (threadIdx.x < kTileCols) {
@@ -189,6 +259,14 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   for (int j = 0; j < 4; ++j) {
     bb[j] = 0.f; tau[j] = 0.f; is2[j] = 1.f; K1[j] = K2[j] = K3[j] = 0.f;
   }
+#pragma unroll
+  for (int k = 0; k < (KC > 0 ? KC : 1); ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) wc[k][j] = 0.f;
+#pragma unroll
+  for (int k = 0; k < (KG > 0 ? KG : 1); ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xg[k][j] = 0.f;
   if (in_ld) {
     if (LOSS && a.eff) {
       const float4 v1 = *reinterpret_cast<const float4*>(a.eff + g0);
@@ -214,17 +292,8 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       bb[0] = vb.x; bb[1] = vb.y; bb[2] = vb.z; bb[3] = vb.w;
       tau[0] = vt.x; tau[1] = vt.y; tau[2] = vt.z; tau[3] = vt.w;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) is2[j] = __expf(-2.0f * tau[j]);
+      for (int j = 0; j < 4; ++j) is2[j] = fast_exp(-2.0f * tau[j]);
     }
-  } else {
-#pragma unroll
-    for (int k = 0; k < KC; ++k)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) wc[k][j] = 0.f;
-#pragma unroll
-    for (int k = 0; k < KG; ++k)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) xg[k][j] = 0.f;
   }
   __syncthreads();  // s_L visible
 
@@ -234,31 +303,18 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  const int64_t row_begin = (int64_t)chunk * a.rows_per_cta;
-  const int64_t row_end = min(row_begin + (int64_t)a.rows_per_cta, a.Nc);
-  const int64_t plane = a.Nc * a.ld;
-  const int64_t mplane = (int64_t)a.M * plane;
   const uint32_t stream0 = brie_stream_word(BRIE_PHASE_TRAIN, (uint32_t)a.model_id[m], 0u);
   const uint32_t ev0 = (uint32_t)(a.event_offset + (int64_t)tile * kTileCols);
-  const bool has_c3 = a.c[2] != nullptr;
   const uint32_t lt_mask = (1u << lane) - 1u;
+  const bool all_act = act4 == 0x01010101u;
 
-  for (int64_t row = row_begin + warp; row < row_end; row += kWarps) {
-    const int64_t off = row * a.ld + g0;            // into one (Nc, ld) plane
-    const int64_t moff = (int64_t)m * plane + off;  // into a (M, Nc, ld) array
-    float4 zmu = make_float4(0.f, 0.f, 0.f, 0.f), zlam = zmu, zm1 = zmu, zv1 = zmu, zm2 = zmu, zv2 = zmu;
-    float4 zc1 = zmu, zc2 = zmu, zc3 = zmu;
-    if (in_ld) {
-      zmu = __ldcs(reinterpret_cast<const float4*>(a.Zl + moff));
-      zlam = __ldcs(reinterpret_cast<const float4*>(a.Zs + moff));
-      zc1 = __ldg(reinterpret_cast<const float4*>(a.c[0] + off));
-      zc2 = __ldg(reinterpret_cast<const float4*>(a.c[1] + off));
-      if (has_c3) zc3 = __ldg(reinterpret_cast<const float4*>(a.c[2] + off));
-      zm1 = __ldcs(reinterpret_cast<const float4*>(a.aZ + moff));
-      zv1 = __ldcs(reinterpret_cast<const float4*>(a.aZ + mplane + moff));
-      zm2 = __ldcs(reinterpret_cast<const float4*>(a.aZ + 2 * mplane + moff));
-      zv2 = __ldcs(reinterpret_cast<const float4*>(a.aZ + 3 * mplane + moff));
-    }
+  int stage = 0;
+  for (int64_t row = row_begin + warp; row < row_end; row += kWarps, stage ^= 1) {
+    issue_row(row + kWarps, stage ^ 1);   // prefetch the next row (zero-size copies past the end)
+    cp_async_wait<1>();                   // this row's group has landed
+    const float4* st = reinterpret_cast<const float4*>(s_ring + stage * (kRingArrays * kTileCols)) + lane;
+    const float4 zmu = st[0 * (kTileCols / 4)], zlam = st[1 * (kTileCols / 4)];
+    const float4 zc1 = st[2 * (kTileCols / 4)], zc2 = st[3 * (kTileCols / 4)], zc3 = st[4 * (kTileCols / 4)];
     float mu[4] = {zmu.x, zmu.y, zmu.z, zmu.w}, lam[4] = {zlam.x, zlam.y, zlam.z, zlam.w};
     const float c1[4] = {zc1.x, zc1.y, zc1.z, zc1.w}, c2[4] = {zc2.x, zc2.y, zc2.z, zc2.w};
     const float c3[4] = {zc3.x, zc3.y, zc3.z, zc3.w};
@@ -273,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     if (CELL) {
       b_row = __ldg(a.b + (int64_t)m * a.Nc + row);
       tau_row = __ldg(a.tau + (int64_t)m * a.Nc + row);
-      is2_row = __expf(-2.0f * tau_row);
+      is2_row = fast_exp(-2.0f * tau_row);
     }
     float cacc[NCELL > 0 ? NCELL : 1];
 #pragma unroll
@@ -292,15 +348,15 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 #pragma unroll
       for (int k = 0; k < KG; ++k) pm = fmaf(wg[k], xg[k][j], pm);
       const float d = lam[j] - tj;
-      const float e2 = __expf(2.0f * d);  // s^2 / sigma^2
+      const float e2 = ex2_approx((2.0f * kLog2e) * d);  // s^2 / sigma^2
       const float diff = mu[j] - pm;
-      const float r = diff * i2;          // (mu - m) / sigma^2
-      const float q2 = diff * r;          // ((mu - m) / sigma)^2
+      const float r = diff * i2;                         // (mu - m) / sigma^2
+      const float q2 = diff * r;                         // ((mu - m) / sigma)^2
       gmu[j] = r;
       glam[j] = e2 - 1.0f;
       ll[j] = 0.f;
       if (c1[j] + c2[j] + c3[j] > 0.f) nz |= 1u << j;
-      const float gt = 1.0f - q2 - e2;    // d loss / d sigma_log
+      const float gt = 1.0f - q2 - e2;                   // d loss / d sigma_log
 #pragma unroll
       for (int k = 0; k < KC; ++k) acc[k][j] = fmaf(-xc[k], r, acc[k][j]);
       if (!CELL) {
@@ -329,7 +385,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       for (int j = 0; j < 4; ++j) {
         if ((nz >> j) & 1u) {
           q[0][pos] = mu[j];
-          q[1][pos] = __expf(lam[j]);
+          q[1][pos] = fast_exp(lam[j]);
           q[2][pos] = c1[j];
           q[3][pos] = c2[j];
           q[4][pos] = c1[j] + c2[j] + c3[j];
@@ -369,16 +425,28 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 
     // ---- phase C: Adam on Z_loc / Z_std_log, clip, store ----
     if (in_ld && act4 != 0) {
+      const float4 zm1 = st[5 * (kTileCols / 4)], zv1 = st[6 * (kTileCols / 4)];
+      const float4 zm2 = st[7 * (kTileCols / 4)], zv2 = st[8 * (kTileCols / 4)];
       float m1[4] = {zm1.x, zm1.y, zm1.z, zm1.w}, v1[4] = {zv1.x, zv1.y, zv1.z, zv1.w};
       float m2[4] = {zm2.x, zm2.y, zm2.z, zm2.w}, v2[4] = {zv2.x, zv2.y, zv2.z, zv2.w};
+      if (all_act) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if ((act4 >> (8 * j)) & 0xffu) {
+        for (int j = 0; j < 4; ++j) {
           adam_update(mu[j], m1[j], v1[j], gmu[j], a.alpha);
           adam_update(lam[j], m2[j], v2[j], glam[j], a.alpha);
           mu[j] = clip9(mu[j]);  // Variable constraint (model_TFProb.py:80-81)
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if ((act4 >> (8 * j)) & 0xffu) {
+            adam_update(mu[j], m1[j], v1[j], gmu[j], a.alpha);
+            adam_update(lam[j], m2[j], v2[j], glam[j], a.alpha);
+            mu[j] = clip9(mu[j]);
+          }
+        }
       }
+      const int64_t moff = (int64_t)m * plane + row * a.ld + g0;
       __stcs(reinterpret_cast<float4*>(a.Zl + moff), make_float4(mu[0], mu[1], mu[2], mu[3]));
       __stcs(reinterpret_cast<float4*>(a.Zs + moff), make_float4(lam[0], lam[1], lam[2], lam[3]));
       __stcs(reinterpret_cast<float4*>(a.aZ + moff), make_float4(m1[0], m1[1], m1[2], m1[3]));
@@ -394,10 +462,11 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       }
     }
   }
+  cp_async_wait<0>();
 
   if (NEV > 0) {
     __syncthreads();  // all warps are done with their queues; reuse the memory for the reduction
-    float(*red)[kTileCols] = reinterpret_cast<float(*)[kTileCols]>(&s_queue[0][0][0]);
+    float(*red)[kTileCols] = reinterpret_cast<float(*)[kTileCols]>(smem + kWarps * kRingStages * kRingArrays * kTileCols);
     const int64_t gcol = (int64_t)tile * kTileCols + threadIdx.x;
 #pragma unroll
     for (int i = 0; i < NEV; ++i) {

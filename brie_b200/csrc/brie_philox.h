@@ -56,7 +56,12 @@ BRIE_HD void brie_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t 
 }
 
 BRIE_HD float brie_u01(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+  // same value without an int->float conversion: [1,2) mantissa trick, exact subtraction
+  return __uint_as_float(0x3f800000u | (x >> 9)) - 0.99999994039535522f;  // 1 - 2^-24
+#else
   return ((float)(x >> 9) + 0.5f) * 1.1920928955078125e-07f;  // 2^-23
+#endif
 }
 
 // One Box-Muller pair.  On the device the fast SFU paths are used (lg2/sin/cos
@@ -66,9 +71,12 @@ BRIE_HD float brie_u01(uint32_t x) {
 BRIE_HD void brie_box_muller(uint32_t a, uint32_t b, float* n0, float* n1) {
   const float u1 = brie_u01(a), u2 = brie_u01(b);
 #if defined(__CUDA_ARCH__)
-  const float r = sqrtf(-2.0f * __logf(u1));
-  float sn, cs;
-  __sincosf(6.283185307179586f * u2, &sn, &cs);
+  float lg, r, sn, cs;
+  const float t = 6.283185307179586f * u2;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u1));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg));  // -2 ln u1
+  asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sn) : "f"(t));
+  asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cs) : "f"(t));
 #else
   const float r = sqrtf(-2.0f * logf(u1));
   const float t = 6.283185307179586f * u2;
