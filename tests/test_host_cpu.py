@@ -1,0 +1,163 @@
+"""CPU tests of the host-side product code: the C-ABI library loads and exports every
+declared symbol (no compute without a GPU), argument validation, host noise dump, the
+reference-side helpers against golden vectors from the reference, sharding logic under
+a 2-process gloo group."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import philox_np as px
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = np.load(os.path.join(ROOT, "tests", "golden", "reference_vectors.npz"), allow_pickle=True)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from brie_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "brie_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(brie_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "missing export: " + name
+    assert declared == set(_lib.SYMBOLS), "ctypes table and header disagree"
+    assert lib.brie_abi_version() == 1
+
+
+def test_struct_layout_matches_header():
+    from brie_b200 import _lib
+    assert C.sizeof(_lib.FitDesc) == 4 * 8 + 8 + 10 * 4 + 32 * 4 + 32 * 4
+    assert C.sizeof(_lib.FitBuffers) == 17 * 8
+    assert C.sizeof(_lib.FitSizes) == 2 * 8 + 4 * 4
+
+
+def _desc(**kw):
+    from brie_b200 import _lib
+    d = _lib.FitDesc()
+    d.n_cells, d.n_events, d.ld, d.event_offset, d.seed = 100, 50, 64, 0, 1
+    d.n_models, d.Kc, d.Kg, d.mc_size, d.n_layers = 1, 1, 0, 3, 3
+    d.has_efflen, d.cell_mode, d.train_intercept, d.train_sigma, d.trace_cap = 1, 0, 1, 1, 8
+    d.xc_mask[0] = 1
+    for k, v in kw.items():
+        setattr(d, k, v)
+    return d
+
+
+def test_create_validates_arguments(lib):
+    from brie_b200 import _lib
+    h = C.c_void_p()
+    assert lib.brie_fit_create(C.byref(_desc()), C.byref(h)) == 0
+    sz = _lib.FitSizes()
+    assert lib.brie_fit_get_sizes(h, C.byref(sz)) == 0
+    assert sz.scratch_bytes > 0 and sz.n_col_tiles == 1 and sz.n_row_chunks * sz.rows_per_cta >= 100
+    # not bound -> error code + message, no crash
+    assert lib.brie_fit_run_steps(h, 1, -1, None) < 0
+    assert b"not bound" in lib.brie_last_error()
+    lib.brie_fit_destroy(h)
+    for bad in (dict(ld=50), dict(ld=62), dict(Kc=3), dict(Kg=5), dict(n_models=0), dict(n_models=33),
+                dict(mc_size=0), dict(n_layers=4), dict(n_cells=0), dict(event_offset=-1)):
+        assert lib.brie_fit_create(C.byref(_desc(**bad)), C.byref(h)) < 0, bad
+        assert len(lib.brie_last_error()) > 0
+    d = _desc()
+    d.xc_mask[0] = 2                      # bit beyond Kc
+    assert lib.brie_fit_create(C.byref(d), C.byref(h)) < 0
+
+
+def test_host_normals_match_numpy_spec(lib):
+    from brie_b200 import _lib
+    S, R, Cn, off = 5, 7, 19, 4000
+    out = np.empty((S, R, Cn), np.float32)
+    _lib.check(lib.brie_philox_normals_host(1234567890123, 1, 9, 77, S, R, Cn, off, out.ctypes.data))
+    ref = px.normal_field(R, Cn, 77, 1, 9, 1234567890123, S, col_offset=off)
+    assert np.abs(out - ref).max() < 2e-6
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from brie_b200.engine import FitEngine
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        FitEngine([np.zeros((4, 4), np.float32)] * 2)
+
+
+def test_match_against_reference_golden():
+    from brie_b200.utils.base_utils import match
+    idx = match(GOLD['match_ref'], GOLD['match_new'])
+    got = np.array([-1 if v is None else int(v) for v in idx])
+    assert np.array_equal(got, GOLD['match_idx'])
+    f = idx.astype(float)                 # quant.py:53-55 idiom
+    assert np.array_equal(f == f, got >= 0)
+
+
+def test_filter_genes_against_reference_golden():
+    from brie_b200.utils.preprocessing import filter_genes
+    from brie_b200.utils.anndata_lite import AnnDataLite
+    from scipy.sparse import csc_matrix
+    for wrap in (lambda x: x, csc_matrix):
+        ad = AnnDataLite(X=GOLD['fg_l1'] + GOLD['fg_l2'] + GOLD['fg_l3'],
+                         layers={'isoform1': wrap(GOLD['fg_l1']), 'isoform2': wrap(GOLD['fg_l2']),
+                                 'ambiguous': wrap(GOLD['fg_l3'])})
+        out = filter_genes(ad, min_counts=50, min_counts_uniq=10, min_cells_uniq=30, min_MIF_uniq=0.001, copy=True)
+        assert out.shape == (80, int(GOLD['fg_subset'].sum()))
+        assert np.array_equal(np.asarray(out.var['n_counts']), GOLD['fg_n_counts'])
+        assert np.array_equal(np.asarray(out.var['n_counts_uniq']), GOLD['fg_n_counts_uniq'])
+        l1 = out.layers['isoform1']
+        l1 = l1.toarray() if hasattr(l1, 'toarray') else l1
+        assert np.array_equal(l1, GOLD['fg_l1'][:, GOLD['fg_subset']])
+        assert ad.shape == (80, 120)      # copy=True leaves the input alone
+
+
+def test_fdr_bh_matches_oracle():
+    from brie_b200.models.model_wrap import fdr_bh
+    from oracle.brie2_oracle import fdr_bh as ofdr
+    rng = np.random.default_rng(0)
+    p = rng.uniform(size=200) ** 3
+    p[:5] = p[5:10]                       # ties
+    assert np.allclose(fdr_bh(p), ofdr(p))
+    assert fdr_bh(np.array([])).size == 0
+
+
+def test_event_shards_properties():
+    from brie_b200.sharding import event_shards
+    for n, w, g in [(5000, 8, 100), (5000, 3, 100), (20000, 8, 1), (17, 4, 5), (3, 8, 1), (1000, 1, 7)]:
+        sh = event_shards(n, w, g)
+        assert len(sh) == w and sh[0][0] == 0 and sh[-1][1] == n
+        for (a, b), (c, d) in zip(sh[:-1], sh[1:]):
+            assert b == c and a <= b
+        assert all(a % g == 0 for a, _ in sh if a < n)
+        sizes = [-(-(b - a) // g) for a, b in sh]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_sharded_gather_two_process_gloo(tmp_path):
+    """world_size 2 on CPU (gloo): each rank owns an aligned event shard, results are gathered
+    along the event axis and equal the un-sharded array."""
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch.distributed as dist
+from brie_b200.sharding import event_shards, gather_event_axis
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+Nc, Ng, gs = 7, 53, 5
+full = np.arange(Nc * Ng, dtype=np.float32).reshape(Nc, Ng)
+a, b = event_shards(Ng, w, gs)[r]
+got = gather_event_axis(full[:, a:b].copy(), 1)
+lg = gather_event_axis(full[0, a:b].copy(), 0)
+assert np.array_equal(got, full) and np.array_equal(lg, full[0])
+dist.destroy_process_group()
+print("rank", r, "ok")
+''' % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
