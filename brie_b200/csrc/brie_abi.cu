@@ -377,7 +377,7 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
       e.active = f->buf.active;
       e.trace = f->buf.loss_trace;
       for (int m = 0; m < M; ++m) e.xc_mask[m] = d.xc_mask[m];
-      const dim3 g2((unsigned)ceil_div(d.n_events, 256), M);
+      const dim3 g2((unsigned)ceil_div(d.n_events, 32), M);
       event_update_kernel<<<g2, 256, 0, s>>>(e);
       BRIE_CUDA(cudaGetLastError());
       f->launches += 1;

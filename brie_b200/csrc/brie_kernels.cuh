@@ -186,11 +186,11 @@ struct StepTraits {
 //     samples (Philox + Box-Muller + likelihood gradient) -- zero-count elements,
 //     80-87 % of real data, cost nothing here and the lanes stay converged;
 //   C (dense): owners read their MC sums back, Adam-update and store (16 B stores).
-constexpr int kQueueFields = 6;   // mu, s, c1, c2, n, column  ->  results overwrite c1, c2, n
+constexpr int kQueueFields = 6;   // mu, s, c1, c2, c3, column  ->  results overwrite c1, c2, c3
 constexpr int kRingArrays = 9;    // Z_loc, Z_std_log, c1, c2, c3, m_loc, v_loc, m_std, v_std
 constexpr int kRingStages = 2;
 constexpr int kStepSmemFloats =
-    kWarps * kRingStages * kRingArrays * kTileCols + kWarps * kQueueFields * kTileCols + 3 * kTileCols;
+    kWarps * kRingStages * kRingArrays * kTileCols + kWarps * kQueueFields * kTileCols + 6 * kTileCols;
 constexpr int kStepSmemBytes = kStepSmemFloats * 4;
 
 template <int KC, int KG, bool CELL, bool LOSS>
@@ -250,14 +250,17 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     float l1 = 1.f, l2 = 1.f, l3 = 0.f;
     if (a.eff && g < a.ld) { l1 = a.eff[g]; l2 = a.eff[a.ld + g]; l3 = a.eff[2 * a.ld + g]; }
     s_L[0][threadIdx.x] = l1; s_L[1][threadIdx.x] = l2; s_L[2][threadIdx.x] = l3;
+    if (LOSS) {  // log lengths for the constant part of the log-likelihood (0 * log 0 never occurs: eff > 0)
+      s_L[3][threadIdx.x] = logf(l1); s_L[4][threadIdx.x] = logf(l2);
+      s_L[5][threadIdx.x] = a.eff ? logf(l3) : 0.f;
+    }
   }
-  float K1[4], K2[4], K3[4];
   float wc[KC > 0 ? KC : 1][4];
   float xg[KG > 0 ? KG : 1][4];
   float bb[4], tau[4], is2[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    bb[j] = 0.f; tau[j] = 0.f; is2[j] = 1.f; K1[j] = K2[j] = K3[j] = 0.f;
+    bb[j] = 0.f; tau[j] = 0.f; is2[j] = 1.f;
   }
 #pragma unroll
   for (int k = 0; k < (KC > 0 ? KC : 1); ++k)
@@ -268,14 +271,6 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) xg[k][j] = 0.f;
   if (in_ld) {
-    if (LOSS && a.eff) {
-      const float4 v1 = *reinterpret_cast<const float4*>(a.eff + g0);
-      const float4 v2 = *reinterpret_cast<const float4*>(a.eff + a.ld + g0);
-      const float4 v3 = *reinterpret_cast<const float4*>(a.eff + 2 * a.ld + g0);
-      K1[0] = logf(v1.x); K1[1] = logf(v1.y); K1[2] = logf(v1.z); K1[3] = logf(v1.w);
-      K2[0] = logf(v2.x); K2[1] = logf(v2.y); K2[2] = logf(v2.z); K2[3] = logf(v2.w);
-      K3[0] = logf(v3.x); K3[1] = logf(v3.y); K3[2] = logf(v3.z); K3[3] = logf(v3.w);
-    }
 #pragma unroll
     for (int k = 0; k < KC; ++k) {
       const float4 v = *reinterpret_cast<const float4*>(a.Wc + ((int64_t)m * KC + k) * a.ld + g0);
@@ -388,14 +383,15 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
           q[1][pos] = fast_exp(lam[j]);
           q[2][pos] = c1[j];
           q[3][pos] = c2[j];
-          q[4][pos] = c1[j] + c2[j] + c3[j];
+          q[4][pos] = c3[j];
           q[5][pos] = __int_as_float(lane * 4 + j);
           ++pos;
         }
       }
       __syncwarp();
       for (int k = lane; k < n_items; k += 32) {
-        const float imu = q[0][k], is = q[1][k], ic1 = q[2][k], ic2 = q[3][k], in = q[4][k];
+        const float imu = q[0][k], is = q[1][k], ic1 = q[2][k], ic2 = q[3][k], ic3 = q[4][k];
+        const float in = ic1 + ic2 + ic3;
         const int col = __float_as_int(q[5][k]);
         const float l1 = s_L[0][col], l2 = s_L[1][col], l3 = s_L[2][col];
         float gs, ge, ls;
@@ -403,7 +399,8 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
                          a.step, stream0, a.seed, gs, ge, ls);
         q[2][k] = gs * a.inv_S;
         q[3][k] = ge * is * a.inv_S;
-        if (LOSS) q[4][k] = ls * a.inv_S;
+        if (LOSS)
+          q[4][k] = fmaf(ls, a.inv_S, fmaf(ic1, s_L[3][col], fmaf(ic2, s_L[4][col], ic3 * s_L[5][col])));
       }
       __syncwarp();
       pos = base;
@@ -412,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
         if ((nz >> j) & 1u) {
           gmu[j] -= q[2][pos];
           glam[j] -= q[3][pos];
-          if (LOSS) ll[j] = q[4][pos] + fmaf(c1[j], K1[j], fmaf(c2[j], K2[j], c3[j] * K3[j]));
+          if (LOSS) ll[j] = q[4][pos];
           ++pos;
         }
       }
@@ -500,18 +497,32 @@ struct EventArgs {
   uint32_t xc_mask[kMaxModels];
 };
 
+constexpr int kMaxNEV = 12;  // BRIE_MAX_KC + 2 + 2
+
+// block = 8 warps x 32 events: warp w sums row chunks w, w+8, ... (coalesced 128-byte rows of the
+// partial buffer), warp 0 combines the 8 sub-sums in fixed order (f64) and applies the updates.
 __global__ void __launch_bounds__(256) event_update_kernel(const EventArgs a) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t g = (int64_t)blockIdx.x * 32 + lane;
   const int m = blockIdx.y;
-  if (g >= a.Ng) return;
-  if (!a.active[(int64_t)m * a.ld + g]) return;
-  const int64_t mstride = (int64_t)a.M * (a.KC + 2) * a.ld;
+  __shared__ float s_part[8][kMaxNEV][32];
+  const bool ok = g < a.Ng && a.active[(int64_t)m * a.ld + g] != 0;
+  if (ok) {
+    for (int i = 0; i < a.NEV; ++i) {
+      float s = 0.f;
+      for (int c = w; c < a.n_chunks; c += 8) s += a.part_ev[(((int64_t)c * a.M + m) * a.NEV + i) * a.ld + g];
+      s_part[w][i][lane] = s;
+    }
+  }
+  __syncthreads();
+  if (w != 0 || !ok) return;
   auto red = [&](int i) {
     double s = 0.0;
-    for (int c = 0; c < a.n_chunks; ++c)
-      s += (double)a.part_ev[(((int64_t)c * a.M + m) * a.NEV + i) * a.ld + g];
+#pragma unroll
+    for (int ww = 0; ww < 8; ++ww) s += (double)s_part[ww][i][lane];
     return s;
   };
+  const int64_t mstride = (int64_t)a.M * (a.KC + 2) * a.ld;
   for (int k = 0; k < a.KC; ++k) {
     if (!((a.xc_mask[m] >> k) & 1u)) continue;
     const float grad = (float)red(k);

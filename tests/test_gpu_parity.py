@@ -13,7 +13,7 @@ import pytest
 from oracle import philox_np as px
 from oracle.brie2_oracle import OracleBRIE2, OracleInit, add_pseudo_count, oracle_fit_matrix
 
-from util import device_eps_provider, make_problem
+from util import device_eps_provider, make_lrt_problem, make_problem
 
 pytestmark = pytest.mark.gpu
 
@@ -167,14 +167,18 @@ def test_loss_gene_eval_parity():
     assert np.abs(lg - ref).max() <= 2e-5 * np.abs(ref).max()
 
 
-def test_full_fit_with_lrt_matches_oracle():
+@pytest.mark.parametrize("kind", ["planted_dense", "sparse_null"])
+def test_full_fit_with_lrt_matches_oracle(kind):
     """fit_BRIE_matrix end to end (schedule, convergence extension, loss_gene, LRT, FDR)
     against oracle_fit_matrix with the same noise."""
     from brie_b200.models import fit_BRIE_matrix
-    Nc, Ng, seed = 120, 48, 21
-    data, effLen, Xc, _ = make_problem(Nc, Ng, 1, 0, True, 3, seed=8)
-    # plant a strong effect of the covariate on a third of the events
-    rng = np.random.default_rng(0)
+    Nc, Ng, seed = 150, 48, 21
+    if kind == "planted_dense":
+        # planted covariate effects of mixed strength so the LRT has calls to agree on
+        data, effLen, Xc, _ = make_lrt_problem(Nc, Ng, seed=8)
+    else:
+        # simulator-style sparse counts (16 % non-zero), no real effect: the hard case for float32
+        data, effLen, Xc, _ = make_problem(Nc, Ng, 1, 0, True, 3, seed=8)
     kw = dict(min_iter=600, max_iter=1600, add_iter=500, MC_size=3, n_eval=40)
     res = fit_BRIE_matrix([x.copy() for x in data], Xc=Xc, effLen=effLen, intercept=None, intercept_mode='gene',
                           LRT_index=None, seed=seed, **kw)
@@ -193,10 +197,21 @@ def test_full_fit_with_lrt_matches_oracle():
     try:
         ref = oracle_fit_matrix([x.copy() for x in data], Xc=Xc, effLen=effLen, intercept=None,
                                 intercept_mode='gene', LRT_index=None, dtype=np.float32, seed=seed, **kw)
+        ref64 = oracle_fit_matrix([x.copy() for x in data], Xc=Xc, effLen=effLen, intercept=None,
+                                  intercept_mode='gene', LRT_index=None, dtype=np.float64, seed=seed, **kw)
     finally:
         ob.OracleBRIE2.eps = orig
     assert list(res.n_iter[:, 0]) == list(ref.n_iter)
-    assert np.abs(res.Psi - ref.Psi).max() < 1e-3
+    # Psi: 1e-3 absolute for the bulk against the float32 restatement; the single worst element is
+    # bounded by float32's own noise floor on this problem = |oracle32 - oracle64| (1.7e-3 here: Adam's
+    # 1/sqrt(v) amplifies rounding where a gradient crosses zero), not by a fixed 1e-3
+    dpsi = np.abs(res.Psi - ref.Psi)
+    envelope = np.abs(ref.Psi - ref64.Psi).max()
+    print("Psi: q99.9 %.2e max %.2e | f32-vs-f64 oracle envelope %.2e | vs f64 %.2e" % (
+        np.quantile(dpsi, 0.999), dpsi.max(), envelope, np.abs(res.Psi - ref64.Psi).max()))
+    assert np.quantile(dpsi, 0.95) < 1e-3 and np.median(dpsi) < 1e-4
+    assert dpsi.max() <= max(1e-3, envelope)                      # as close as float32 itself allows
+    assert np.abs(res.Psi - ref64.Psi).max() <= max(1e-3, 2 * envelope)
     assert np.abs(res.loss_gene - ref.loss_gene).max() <= 1e-4 * np.abs(ref.loss_gene).max()
     assert abs(res.losses[-1] - ref.losses[-1]) <= 1e-4 * abs(ref.losses[-1])
     # LRT statistic: 1e-3 relative wherever it can matter for a call (p < 0.05 needs gain > 1.92);
@@ -208,3 +223,6 @@ def test_full_fit_with_lrt_matches_oracle():
     assert rel.max(initial=0) <= 1e-3
     assert np.abs(res.ELBO_gain - ref.ELBO_gain).max() < 1e-2
     assert ((res.fdr < 0.05) == (ref.fdr < 0.05)).all()
+    print("DAS calls at FDR<0.05: %d of %d" % ((ref.fdr < 0.05).sum(), ref.fdr.size))
+    if kind == "planted_dense":
+        assert (ref.fdr < 0.05).sum() >= 3

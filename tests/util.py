@@ -33,3 +33,25 @@ def make_problem(Nc, Ng, Kc, Kg, eff=True, n_layers=3, seed=1, design_seed=0):
     Xg = rng.standard_normal((Ng, Kg)).astype(np.float32)
     data = [x.copy() for x in d['layers']]
     return data, d['effLen'], Xc, Xg
+
+
+def make_lrt_problem(Nc=150, Ng=48, seed=8):
+    """Denser reads and planted covariate effects of mixed strength, so that an LRT at this
+    small size produces both significant and non-significant calls."""
+    rng = np.random.default_rng(seed)
+    x = rng.binomial(1, 0.5, Nc).astype(np.float32)
+    beta = rng.choice([0.0, 0.0, 0.8, 2.5], Ng)
+    b = rng.normal(0, 1.0, Ng)
+    z = b[None, :] + x[:, None] * beta[None, :] + rng.normal(0, 0.5, (Nc, Ng))
+    psi = 1 / (1 + np.exp(-z))
+    ex = rng.uniform(50, 300, (Ng, 3))
+    L1, L2, L3 = ex[:, 1] + 72, np.full(Ng, 72.0), ex[:, 0] + ex[:, 2] - 16
+    effLen = np.zeros((Ng, 6), np.float32)
+    effLen[:, 0], effLen[:, 2], effLen[:, 4], effLen[:, 5] = L1, L3, L2, L3
+    n = rng.poisson(25, (Nc, Ng)) * (rng.uniform(size=(Nc, Ng)) < 0.7)
+    p1, p2 = psi * L1, (1 - psi) * L2
+    D = p1 + p2 + L3
+    c1 = rng.binomial(n, p1 / D)
+    c2 = rng.binomial(n - c1, p2 / (D - p1))
+    c3 = n - c1 - c2
+    return [c1.astype(np.float32), c2.astype(np.float32), c3.astype(np.float32)], effLen, x[:, None], beta
