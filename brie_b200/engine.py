@@ -299,8 +299,8 @@ class FitEngine:
                 for g in range(NG):
                     if active[m, g]:
                         L = traces[m][g]
-                        with np.errstate(invalid='ignore'):
-                            cond = (L[-d2:-d1].mean() - L[-d1:].mean() > epsilon_conv) if L.size else False
+                        a_, b_ = L[-d2:-d1], L[-d1:]      # an empty window compares False, as NaN does in the reference
+                        cond = (a_.mean() - b_.mean() > epsilon_conv) if (a_.size and b_.size) else False
                         active[m, g] = bool(cond) and n_iter[m, g] < max_iter
             if not active.any():
                 break

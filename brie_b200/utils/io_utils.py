@@ -1,0 +1,90 @@
+"""Count-matrix loaders and the result table (semantics of brie/utils/io_utils.py).
+
+`anndata` / `h5py` are used when importable; otherwise the AnnDataLite duck type and
+its npz persistence stand in (the image has neither package).
+"""
+import numpy as np
+import pandas as pd
+
+try:  # pragma: no cover - not installable in the build image
+    import anndata as _anndata
+except ImportError:
+    _anndata = None
+
+from .anndata_lite import AnnDataLite
+
+
+def _make_adata(**kw):
+    if _anndata is not None:
+        return _anndata.AnnData(**kw)
+    return AnnDataLite(**kw)
+
+
+def read_h5ad(path):
+    if _anndata is not None:
+        return _anndata.read_h5ad(path)
+    if str(path).endswith(".npz"):
+        return AnnDataLite.read_npz(path)
+    raise RuntimeError("brie_b200: reading .h5ad needs the `anndata` package; "
+                       "use the brie .npz count format (read_npz) in this environment")
+
+
+def convert_to_annData(Rmat_dict, effLen_tensor, cell_note, gene_note, fill_missing=True):
+    """Count matrices keyed '0'..'3' + effective-length tensor (Ng, 2, 3) -> AnnData with layers
+    isoform1/isoform2/ambiguous/poorQual, X = 1+2+3, varm['effLen'] (Ng, 6) = [iso1 | iso2],
+    varm['p_ambiguous'] (io_utils.py:12-52)."""
+    Rmat = {k: v.astype(np.float32) for k, v in Rmat_dict.items()}
+    if fill_missing:
+        shape = next(iter(Rmat.values())).shape
+        for k in ['0', '1', '2', '3']:
+            if k not in Rmat:
+                print("key %s not exist in .mtx file, fill with zeros." % (k))
+                Rmat[k] = np.zeros(shape, dtype=np.float32)
+    layers = {'isoform1': Rmat['1'], 'isoform2': Rmat['2'], 'ambiguous': Rmat['3'], 'poorQual': Rmat['0']}
+    obs = pd.DataFrame(cell_note[1:, :], index=cell_note[1:, 0], columns=cell_note[0, :])
+    var = pd.DataFrame(gene_note[1:, :], index=gene_note[1:, 0], columns=gene_note[0, :])
+    prob = effLen_tensor / effLen_tensor.sum(2, keepdims=True)
+    varm = {'effLen': np.append(effLen_tensor[:, 0, :], effLen_tensor[:, 1, :], axis=1),
+            'p_ambiguous': prob[:, :, 2]}
+    return _make_adata(X=Rmat['1'] + Rmat['2'] + Rmat['3'], obs=obs, var=var, varm=varm, layers=layers)
+
+
+def read_npz(path):
+    """brie-count's npz (keys cell_note, gene_note, Rmat_dict, effLen_tensor; io_utils.py:55-65)."""
+    dat = np.load(path, allow_pickle=True)
+    return convert_to_annData(dat['Rmat_dict'].item(), dat['effLen_tensor'], dat['cell_note'], dat['gene_note'])
+
+
+def write_npz_counts(path, layers, effLen_tensor, cell_ids, gene_ids):
+    """Writer for the same npz format (used by tests and the synthetic-data tools)."""
+    from scipy.sparse import csc_matrix
+    keys = {'isoform1': '1', 'isoform2': '2', 'ambiguous': '3'}
+    Rmat = {keys[k]: csc_matrix(v) for k, v in layers.items()}
+    cell_note = np.array([["cellID"]] + [[c] for c in cell_ids], dtype=object)
+    gene_note = np.array([["GeneID"]] + [[g] for g in gene_ids], dtype=object)
+    np.savez(path, Rmat_dict=np.array(Rmat, dtype=object), effLen_tensor=effLen_tensor,
+             cell_note=cell_note, gene_note=gene_note)
+
+
+def dump_results(adata):
+    """Result table of detected splicing phenotypes (io_utils.py:163-199), including the
+    reference's column naming (`_ceoff`) and its positional indexing of cell_coeff."""
+    X = adata.X
+    df = adata.var[['n_counts', 'n_counts_uniq']].copy()
+    df['n_counts'] = df['n_counts'].astype(int)
+    df['n_counts_uniq'] = df['n_counts_uniq'].astype(int)
+    df['cdr'] = np.asarray((X > 0).mean(0)).reshape(-1)
+    df['intercept'] = adata.varm['intercept'][:, 0] if 'intercept' in adata.varm else [None] * adata.shape[1]
+    df['sigma'] = adata.varm['sigma'][:, 0] if 'sigma' in adata.varm else [None] * adata.shape[1]
+    LRT_index = adata.uns['brie_param']['LRT_index'] if 'brie_param' in adata.uns else []
+    for i in range(len(LRT_index)):
+        _idx = LRT_index[i]
+        if 'Xc_ids' in adata.uns and adata.uns['Xc_ids'] is not None:
+            name = adata.uns['Xc_ids'][_idx]
+        else:
+            name = 'X%d' % i
+        df[name + '_ceoff'] = adata.varm['cell_coeff'][:, i]
+        df[name + '_ELBO_gain'] = adata.varm['ELBO_gain'][:, i]
+        df[name + '_pval'] = adata.varm['pval'][:, i]
+        df[name + '_FDR'] = adata.varm['fdr'][:, i]
+    return df

@@ -1,0 +1,172 @@
+"""GPU tests of the reference-facing API: fitBRIE's event batches as convergence groups,
+the BRIE2 class protocol, the brie-quant driver end to end (BASELINE config C1 style)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle.brie2_oracle as ob
+from oracle.brie2_oracle import oracle_fit_matrix
+from util import device_eps_provider, make_lrt_problem, make_problem
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _patched_oracle(seed, Nc, fn):
+    """Run fn() with OracleBRIE2 drawing the device's noise (per model id / column offset)."""
+    orig = ob.OracleBRIE2.eps
+    ob.OracleBRIE2.eps = lambda self, phase, step, S: device_eps_provider(
+        seed, self.model_id, Nc, self.Ng, self.col_offset)(phase, step, S)
+    try:
+        return fn()
+    finally:
+        ob.OracleBRIE2.eps = orig
+
+
+def test_fitBRIE_groups_match_sequential_reference_batches():
+    """fitBRIE fits all events in one engine but stops each reference batch (ceil(batch_size/Nc)
+    events, model_wrap.py:241-258) independently -- compare with the oracle fitted batch by batch."""
+    from brie_b200.models import fitBRIE
+    from brie_b200.utils.anndata_lite import AnnDataLite
+    Nc, Ng, seed = 100, 70, 4
+    data, effLen, Xc, _ = make_lrt_problem(Nc, Ng, seed=3)
+    ad = AnnDataLite(X=data[0] + data[1] + data[2],
+                     layers={'isoform1': data[0].copy(), 'isoform2': data[1].copy(), 'ambiguous': data[2].copy()},
+                     varm={'effLen': effLen})
+    kw = dict(min_iter=600, max_iter=2100, add_iter=500, MC_size=2, n_eval=20)
+    batch_size = 100 * 30                                  # -> 30 events per batch: groups of 30, 30, 10
+    res = fitBRIE(ad, Xc=Xc, LRT_index=None, intercept_mode='gene', batch_size=batch_size, seed=seed, **kw)
+    assert res.n_iter.shape == (2, 3)
+
+    def run_oracle():
+        out = []
+        for e0 in range(0, Ng, 30):
+            sl = slice(e0, min(e0 + 30, Ng))
+            out.append(oracle_fit_matrix([x[:, sl].copy() for x in data], Xc=Xc, effLen=effLen[sl], LRT_index=None,
+                                         intercept_mode='gene', dtype=np.float32, seed=seed, col_offset=e0, **kw))
+        return out
+    refs = _patched_oracle(seed, Nc, run_oracle)
+    for gi, r in enumerate(refs):
+        assert list(res.n_iter[:, gi]) == list(r.n_iter), "group %d step counts" % gi
+    print("n_iter per (model, group):", res.n_iter.tolist())
+    assert len(set(res.n_iter.reshape(-1).tolist())) > 1, "want groups that stop at different times"
+    Psi = np.concatenate([r.Psi for r in refs], axis=1)
+    gain = np.concatenate([r.ELBO_gain for r in refs], axis=0)
+    fdr_in = np.concatenate([r.pval for r in refs], axis=0)
+    assert np.quantile(np.abs(res.Psi - Psi), 0.99) < 1e-3
+    big = np.abs(gain) > 1.5
+    assert (np.abs(res.ELBO_gain - gain)[big] / np.abs(gain)[big]).max() < 1e-3
+    # uns['brie_losses'] = per-batch traces appended end to end (model_wrap.py:61)
+    want = np.concatenate([r.losses for r in refs])
+    assert ad.uns['brie_losses'].shape == want.shape
+    assert np.abs(ad.uns['brie_losses'] - want).max() <= 1e-4 * np.abs(want).max()
+    # AnnData outputs (model_wrap.py:271-311)
+    assert ad.layers['Psi'].shape == (Nc, Ng) and ad.layers['Psi_95CI'].shape == (Nc, Ng)
+    assert ad.layers['Z_std'].shape == (Nc, Ng)
+    assert ad.varm['cell_coeff'].shape == (Ng, 1) and ad.varm['intercept'].shape == (Ng, 1)
+    assert ad.varm['sigma'].shape == (Ng, 1)
+    for k in ('fdr', 'pval', 'ELBO_gain'):
+        assert ad.varm[k].shape == (Ng, 1)
+    assert np.asarray(ad.var['loss_gene']).shape == (Ng,)
+    assert set(ad.uns['brie_param']) == {'LRT_index', 'base_mode', 'intecept', 'intercept_mode', 'sigma',
+                                         'pseudo_count', 'layer_keys'}
+    # p-values follow from the gains; FDR is computed over ALL events at once per batch in the reference
+    from scipy.stats import chi2
+    assert np.allclose(res.pval, chi2.sf(2 * res.ELBO_gain, df=1))
+
+
+def test_BRIE2_class_protocol_and_null_base_mode():
+    """BRIE2 mirror: constructor / fit / .numpy() attributes; testBase 'null' appends the tested
+    feature's coefficient (model_wrap.py:164-171, 185-187)."""
+    from brie_b200.models import BRIE2, fit_BRIE_matrix, Model_init
+    Nc, Ng = 90, 40
+    data, effLen, Xc, Xg = make_problem(Nc, Ng, 2, 0, True, 3, seed=2)
+    d2 = [x.copy() for x in data]
+    idx = d2[0] + d2[1] > 0
+    for i in range(2):
+        d2[i][idx] += 0.01
+    init = Model_init(Nc, Ng, 2, 0, (1, Ng), (1, Ng), seed=5)
+    m = BRIE2(Nc=Nc, Ng=Ng, Kc=2, Kg=0, effLen=effLen, intercept=None, intercept_mode='gene', init_obj=init)
+    losses = m.fit(d2, Xc=Xc, Xg=None, min_iter=120, max_iter=120, MC_size=2, n_eval=10, verbose=False)
+    assert losses.shape == (20,) and np.isfinite(losses).all()
+    for name, shape in (('sigma', (1, Ng)), ('intercept', (1, Ng)), ('Wc_loc', (2, Ng)), ('Wg_loc', (Nc, 0)),
+                        ('Psi', (Nc, Ng)), ('Z_loc', (Nc, Ng)), ('Z_std', (Nc, Ng)), ('loss_gene', (Ng,))):
+        assert getattr(m, name).numpy().shape == shape, name
+    assert m.Psi95CI.shape == (Nc, Ng) and (m.Psi95CI >= 0).all()
+    assert np.abs(m.Z_loc.numpy()).max() <= 9.0
+    with pytest.raises(NotImplementedError):
+        m.fit(d2, Xc=Xc, target="marginLik")
+
+    res = fit_BRIE_matrix([x.copy() for x in data], Xc=Xc, effLen=effLen, LRT_index=[1], base_mode='null',
+                          intercept_mode='gene', min_iter=120, max_iter=120, MC_size=2, n_eval=10, seed=1)
+    assert res.cell_coeff.shape == (2, Ng)          # base (feature 0) + appended tested feature 1
+    assert res.ELBO_gain.shape == (Ng, 1) and res.n_iter.shape == (2, 1)
+    ref = _patched_oracle(1, Nc, lambda: oracle_fit_matrix(
+        [x.copy() for x in data], Xc=Xc, effLen=effLen, LRT_index=[1], base_mode='null', intercept_mode='gene',
+        dtype=np.float32, min_iter=120, max_iter=120, MC_size=2, n_eval=10, seed=1))
+    assert np.quantile(np.abs(res.Psi - ref.Psi), 0.99) < 1e-3
+    assert np.abs(res.cell_coeff - ref.cell_coeff).max() < 5e-3
+    assert np.abs(res.ELBO_gain - ref.ELBO_gain).max() < 2e-2
+
+
+def test_cell_mode_base_with_gene_mode_refits():
+    """intercept_mode='cell' + LRT: the reference's refits silently fall back to the per-event
+    layout (model_wrap.py:174-178); we reproduce that with a second engine."""
+    from brie_b200.models import fit_BRIE_matrix
+    Nc, Ng = 80, 36
+    data, effLen, Xc, Xg = make_problem(Nc, Ng, 1, 2, False, 2, seed=6)
+    kw = dict(min_iter=120, max_iter=120, MC_size=2, n_eval=10)
+    res = fit_BRIE_matrix([x.copy() for x in data], Xc=Xc, Xg=Xg, intercept_mode='cell', LRT_index=None, seed=2, **kw)
+    assert res.intercept.shape == (Nc, 1) and res.sigma.shape == (Nc, 1) and res.gene_coeff.shape == (Nc, 2)
+    ref = _patched_oracle(2, Nc, lambda: oracle_fit_matrix(
+        [x.copy() for x in data], Xc=Xc, Xg=Xg, intercept_mode='cell', LRT_index=None, dtype=np.float32, seed=2, **kw))
+    assert np.quantile(np.abs(res.Psi - ref.Psi), 0.99) < 1e-3
+    assert np.abs(res.gene_coeff - ref.gene_coeff).max() < 5e-3
+    assert np.abs(res.loss_gene - ref.loss_gene).max() <= 1e-4 * np.abs(ref.loss_gene).max()
+    assert np.abs(res.ELBO_gain - ref.ELBO_gain).max() < 2e-2
+
+
+def test_brie_quant_cli_end_to_end(tmp_path):
+    """BASELINE config C1 in miniature: simulated 2-isoform counts, npz in, brie-quant without and
+    with a cell covariate, result container + TSV out."""
+    from brie_b200.bin.quant import quant
+    from brie_b200.utils import io_utils
+    from brie_b200.utils.anndata_lite import AnnDataLite
+    Nc, Ng = 200, 60
+    data, effLen, Xc, beta = make_lrt_problem(Nc, Ng, seed=11)
+    eff3 = np.zeros((Ng, 2, 3), np.float32)
+    eff3[:, 0, :], eff3[:, 1, :] = effLen[:, :3], effLen[:, 3:]
+    cells = ["cell%03d" % i for i in range(Nc)]
+    genes = ["ENSG%05d" % i for i in range(Ng)]
+    inp = str(tmp_path / "brie_count.npz")
+    io_utils.write_npz_counts(inp, {'isoform1': data[0], 'isoform2': data[1], 'ambiguous': data[2]}, eff3, cells, genes)
+    out = str(tmp_path / "out" / "brie_quant.npz")
+    ad = quant(inp, out_file=out, LRT_index=[], intercept=None, intercept_mode='gene', min_iter=240, max_iter=240,
+               MC_size=3, batch_size=200 * 25)
+    assert os.path.exists(out) and os.path.exists(out.replace(".npz", ".brie_ident.tsv"))
+    assert ad.layers['Psi'].shape == ad.shape and 'ELBO_gain' not in ad.varm
+    back = AnnDataLite.read_npz(out)
+    assert np.array_equal(back.layers['Psi'], ad.layers['Psi'])
+    # with a covariate file (shuffled rows, one unknown cell) and LRT on all features
+    cf = tmp_path / "cells.tsv"
+    order = np.random.default_rng(0).permutation(Nc)
+    with open(cf, "w") as f:
+        f.write("cellID\tgroup\n")
+        f.write("ghost\t1\n")
+        for i in order[:-5]:                                  # 5 cells have no covariate -> dropped
+            f.write("%s\t%d\n" % (cells[i], int(Xc[i, 0])))
+    out2 = str(tmp_path / "out" / "brie_quant_cell.npz")
+    ad2 = quant(inp, cell_file=str(cf), out_file=out2, LRT_index=None, intercept=None, intercept_mode='gene',
+                min_iter=600, max_iter=600, MC_size=3)
+    assert ad2.shape[0] == Nc - 5
+    tsv = open(out2.replace(".npz", ".brie_ident.tsv")).read().splitlines()
+    hdr = tsv[0].split("\t")
+    assert hdr[:6] == ['GeneID', 'n_counts', 'n_counts_uniq', 'cdr', 'intercept', 'sigma']
+    assert hdr[6:] == ['group_ceoff', 'group_ELBO_gain', 'group_pval', 'group_FDR']
+    assert len(tsv) == 1 + ad2.shape[1]
+    # the planted strong effects are called, the nulls mostly not
+    kept = np.array([g in set(ad2.var.index) for g in genes])
+    b = beta[kept]
+    fdr = ad2.varm['fdr'][:, 0]
+    assert (fdr[b > 2] < 0.05).mean() > 0.9 and (fdr[b == 0] < 0.05).mean() < 0.2
