@@ -154,13 +154,14 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
   f->d = d;
   memset(&f->buf, 0, sizeof f->buf);
   const int n_tiles = (int)ceil_div(d.ld, kTileCols);
-  // rows per CTA: enough CTAs for ~4 waves of 2 CTAs/SM when the problem allows it
-  int rows = 128;
+  // rows per CTA: up to 256 (fewer row-chunk partials for event_update_kernel) while keeping
+  // >= ~10 waves of 2 CTAs/SM (tail effect); small problems go down to one row per warp
+  int rows = 256;
   const char* env = getenv("BRIE_ROWS_PER_CTA");
   if (env && atoi(env) > 0) {
     rows = atoi(env);
   } else {
-    const int64_t target = 148 * 2 * 4;
+    const int64_t target = 148 * 2 * 10;
     while (rows > 8 && (int64_t)d.n_models * n_tiles * ceil_div(d.n_cells, rows) < target) rows >>= 1;
   }
   const int64_t n_chunks = ceil_div(d.n_cells, rows);
@@ -524,10 +525,14 @@ int brie_simulate_counts(uint64_t seed, int64_t n_cells, int64_t n_events, int64
                          const float* logit_mean, const float* logit_sd, const float* Xc, const float* Wc,
                          int32_t Kc, const float* efflen3, const float* lam, const float* cdr, float pseudo_count,
                          float* c1, float* c2, float* c3, void* stream) {
-  (void)seed; (void)n_cells; (void)n_events; (void)ld; (void)event_offset; (void)logit_mean; (void)logit_sd;
-  (void)Xc; (void)Wc; (void)Kc; (void)efflen3; (void)lam; (void)cdr; (void)pseudo_count; (void)c1; (void)c2;
-  (void)c3; (void)stream;
-  return fail(BRIE_ERR_UNSUPPORTED, "brie_simulate_counts: not implemented yet");
+  if (n_cells <= 0 || n_events <= 0 || ld < n_events) return fail(BRIE_ERR_ARG, "bad shape");
+  if (!logit_mean || !logit_sd || !lam || !cdr || !c1 || !c2) return fail(BRIE_ERR_ARG, "null argument");
+  if (Kc < 0 || (Kc > 0 && (!Xc || !Wc))) return fail(BRIE_ERR_ARG, "Xc and Wc required when Kc > 0");
+  simulate_counts_kernel<<<grid_1d(n_cells * ld, 256), 256, 0, (cudaStream_t)stream>>>(
+      seed, n_cells, n_events, ld, event_offset, logit_mean, logit_sd, Xc, Wc, Kc, efflen3, lam, cdr, pseudo_count,
+      c1, c2, c3);
+  BRIE_CUDA(cudaGetLastError());
+  return BRIE_OK;
 }
 
 }  // extern "C"

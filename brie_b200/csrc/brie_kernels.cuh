@@ -303,9 +303,32 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   const uint32_t lt_mask = (1u << lane) - 1u;
   const bool all_act = act4 == 0x01010101u;
 
+  // per-row (cell) constants are warp-uniform loads; fetch them one row ahead so their latency
+  // overlaps the current row's work like the ring does for the big arrays
+  float xc_n[KC > 0 ? KC : 1], wg_n[KG > 0 ? KG : 1], b_n = 0.f, tau_n = 0.f;
+  auto load_row_consts = [&](int64_t row) {
+    const int64_t r = row < row_end ? row : row_end - 1;
+#pragma unroll
+    for (int k = 0; k < KC; ++k) xc_n[k] = __ldg(a.Xc + r * KC + k);
+#pragma unroll
+    for (int k = 0; k < KG; ++k) wg_n[k] = __ldg(a.Wg + ((int64_t)m * a.Nc + r) * KG + k);
+    if (CELL) {
+      b_n = __ldg(a.b + (int64_t)m * a.Nc + r);
+      tau_n = __ldg(a.tau + (int64_t)m * a.Nc + r);
+    }
+  };
+  if (row_begin + warp < row_end) load_row_consts(row_begin + warp);
+
   int stage = 0;
   for (int64_t row = row_begin + warp; row < row_end; row += kWarps, stage ^= 1) {
+    float xc[KC > 0 ? KC : 1], wg[KG > 0 ? KG : 1];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) xc[k] = xc_n[k];
+#pragma unroll
+    for (int k = 0; k < KG; ++k) wg[k] = wg_n[k];
+    const float b_row = b_n, tau_row = tau_n;
     issue_row(row + kWarps, stage ^ 1);   // prefetch the next row (zero-size copies past the end)
+    load_row_consts(row + kWarps);
     cp_async_wait<1>();                   // this row's group has landed
     const float4* st = reinterpret_cast<const float4*>(s_ring + stage * (kRingArrays * kTileCols)) + lane;
     const float4 zmu = st[0 * (kTileCols / 4)], zlam = st[1 * (kTileCols / 4)];
@@ -313,19 +336,8 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     float mu[4] = {zmu.x, zmu.y, zmu.z, zmu.w}, lam[4] = {zlam.x, zlam.y, zlam.z, zlam.w};
     const float c1[4] = {zc1.x, zc1.y, zc1.z, zc1.w}, c2[4] = {zc2.x, zc2.y, zc2.z, zc2.w};
     const float c3[4] = {zc3.x, zc3.y, zc3.z, zc3.w};
-    // per-row (cell) constants: warp-uniform loads
-    float xc[KC > 0 ? KC : 1];
-#pragma unroll
-    for (int k = 0; k < KC; ++k) xc[k] = __ldg(a.Xc + row * KC + k);
-    float wg[KG > 0 ? KG : 1];
-#pragma unroll
-    for (int k = 0; k < KG; ++k) wg[k] = __ldg(a.Wg + ((int64_t)m * a.Nc + row) * KG + k);
-    float b_row = 0.f, tau_row = 0.f, is2_row = 1.f;
-    if (CELL) {
-      b_row = __ldg(a.b + (int64_t)m * a.Nc + row);
-      tau_row = __ldg(a.tau + (int64_t)m * a.Nc + row);
-      is2_row = fast_exp(-2.0f * tau_row);
-    }
+    float is2_row = 1.f;
+    if (CELL) is2_row = fast_exp(-2.0f * tau_row);
     float cacc[NCELL > 0 ? NCELL : 1];
 #pragma unroll
     for (int i = 0; i < (NCELL > 0 ? NCELL : 1); ++i) cacc[i] = 0.f;
@@ -768,6 +780,91 @@ __global__ void __launch_bounds__(128) group_trace_kernel(const float* trace, in
     double s = 0.0;
     for (int64_t g = lo; g < hi; ++g) s += (double)row[g];
     out[((int64_t)m * n_groups + grp) * n_slots + slot] = s;
+  }
+}
+
+// Synthetic count generator (bench workloads too large for host RAM).
+// Generative recipe of brie/models/simulator.py:54-73 with psi = logistic(N(., .)) as in
+// simulator/simuPSI.py:129-130: z = mean_g + Xc[c,:] Wc[:,g] + sd_g N(0,1), clipped to +-9
+// (simulator.py:38-39); n ~ Poisson(lam_g) * Bernoulli(cdr_g); (c1,c2,c3) ~ Multinomial(n, phi),
+// phi ~ [psi L1, (1-psi) L2, L3]; pseudo-count as model_wrap.py:113-117.
+#define BRIE_PHASE_SIM 3u
+
+struct SimRng {
+  uint32_t event, cell, stream, ctr;
+  uint64_t seed;
+  uint32_t buf[4];
+  int have;
+  __device__ uint32_t next() {
+    if (have == 0) {
+      brie_philox4x32_10(event, cell, ctr++, stream, (uint32_t)seed, (uint32_t)(seed >> 32), buf);
+      have = 4;
+    }
+    return buf[--have];
+  }
+  __device__ float uniform() { return brie_u01(next()); }
+  __device__ float normal() {
+    float a, b;
+    const uint32_t x = next(), y = next();
+    brie_box_muller(x, y, &a, &b);
+    return a;
+  }
+};
+
+__device__ inline int sim_poisson(SimRng& r, float lam) {
+  if (lam <= 0.f) return 0;
+  if (lam > 40.f) return max(0, (int)rintf(lam + sqrtf(lam) * r.normal()));   // normal approximation in the tail
+  const float limit = expf(-lam);                                            // Knuth's product method
+  int k = 0;
+  float p = r.uniform();
+  while (p > limit && k < 400) { ++k; p *= r.uniform(); }
+  return k;
+}
+
+__device__ inline int sim_binomial(SimRng& r, int n, float p) {
+  if (n <= 0 || p <= 0.f) return 0;
+  if (p >= 1.f) return n;
+  if (n > 96) {
+    const float mu = n * p, sd = sqrtf(n * p * (1.f - p));
+    return min(n, max(0, (int)rintf(mu + sd * r.normal())));
+  }
+  int k = 0;
+  for (int i = 0; i < n; ++i) k += r.uniform() < p;
+  return k;
+}
+
+__global__ void __launch_bounds__(256) simulate_counts_kernel(uint64_t seed, int64_t Nc, int64_t Ng, int64_t ld,
+                                                              int64_t event_offset, const float* mean,
+                                                              const float* sd, const float* Xc, const float* Wc,
+                                                              int Kc, const float* eff, const float* lam,
+                                                              const float* cdr, float pseudo, float* c1,
+                                                              float* c2, float* c3) {
+  const int64_t total = Nc * ld;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i / ld, g = i % ld;
+    float o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    if (g < Ng) {
+      SimRng r;
+      r.event = (uint32_t)(event_offset + g); r.cell = (uint32_t)c; r.stream = brie_stream_word(BRIE_PHASE_SIM, 0u, 0u);
+      r.ctr = 0; r.seed = seed; r.have = 0;
+      const int n = (r.uniform() < cdr[g]) ? sim_poisson(r, lam[g]) : 0;
+      if (n > 0) {
+        float z = mean[g] + sd[g] * r.normal();
+        for (int k = 0; k < Kc; ++k) z = fmaf(Xc[c * Kc + k], Wc[(int64_t)k * ld + g], z);
+        z = fminf(fmaxf(z, -9.f), 9.f);
+        const float psi = 1.f / (1.f + expf(-z));
+        float L1 = 1.f, L2 = 1.f, L3 = 0.f;
+        if (eff) { L1 = eff[g]; L2 = eff[ld + g]; L3 = eff[2 * ld + g]; }
+        const float p1 = psi * L1, p2 = (1.f - psi) * L2, D = p1 + p2 + L3;
+        const int k1 = sim_binomial(r, n, p1 / D);
+        const int k2 = sim_binomial(r, n - k1, p2 / (D - p1));
+        o1 = (float)k1; o2 = (float)k2; o3 = (float)(n - k1 - k2);
+        if (k1 + k2 > 0) { o1 += pseudo; o2 += pseudo; }
+      }
+    }
+    c1[i] = o1; c2[i] = o2;
+    if (c3) c3[i] = o3;
   }
 }
 

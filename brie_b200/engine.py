@@ -55,12 +55,16 @@ class FitEngine:
     def __init__(self, counts, effLen=None, Xc=None, Xg=None, masks=None, model_ids=None,
                  intercept=None, intercept_mode='gene', sigma=None, MC_size=1, seed=0,
                  group_size=None, event_offset=0, n_events_total=None, device=None,
-                 trace_cap=None, dist_group=None):
+                 trace_cap=None, dist_group=None, n_events=None):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("brie_b200: no CUDA device (there is no CPU fallback)")
         self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         Nc, Ng = counts[0].shape
+        if n_events is not None:          # device tensors already padded to (Nc, ld), e.g. from the simulator
+            Ng = int(n_events)
         self.Nc, self.Ng = int(Nc), int(Ng)
         self.ld = _round_up(self.Ng, 32)
         self.event_offset = int(event_offset)
@@ -94,6 +98,9 @@ class FitEngine:
         ld = self.ld
 
         def padded(x):
+            if (torch.is_tensor(x) and x.device == dev and x.dtype == f32 and tuple(x.shape) == (self.Nc, ld)
+                    and x.is_contiguous()):
+                return x                  # zero-copy: caller guarantees zero counts in the padding
             t = torch.zeros((self.Nc, ld), dtype=f32, device=dev)
             src = x if torch.is_tensor(x) else torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32))
             t[:, :self.Ng].copy_(src, non_blocking=True)

@@ -68,3 +68,50 @@ def simulate_counts(Nc, Ng, design='none', seed=0, with_efflen=True, n_layers=3,
         layers.append(c3.astype(np.float32))
     return dict(layers=layers, effLen=effLen, Xc=Xc,
                 truth=dict(psi=psi.astype(np.float32), Wc=Wc, b=b, sigma=sig))
+
+
+def simulate_counts_device(Nc, Ng, design='none', seed=0, with_efflen=True, n_layers=3, effect_frac=0.1,
+                           pseudo_count=0.01, event_offset=0, device="cuda"):
+    """Same recipe as simulate_counts, drawn on the GPU (brie_simulate_counts): the per-event
+    parameters come from numpy (small), the (cells, events) counts never touch host RAM.
+    Returns dict(layers=[device tensors (Nc, ld) with the pseudo-count applied], ld, effLen, Xc, truth)."""
+    import ctypes as C
+    import torch
+    from .. import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(seed)
+    Xc = make_design(Nc, design, rng)
+    Kc = Xc.shape[1]
+    ld = (Ng + 31) // 32 * 32
+    pad = lambda v, fill=0.0: np.concatenate([v, np.full(ld - Ng, fill)]).astype(np.float32)
+    b = rng.normal(0, 3.0, Ng)
+    Wc = rng.standard_normal((Kc, Ng)) * (rng.uniform(size=(1, Ng)) < effect_frac)
+    sig = np.exp(rng.normal(0, 0.5, Ng))
+    if with_efflen:
+        ex = rng.uniform(50, 300, (Ng, 3))
+        L = np.stack([ex[:, 1] + 72, np.full(Ng, 72.0), ex[:, 0] + ex[:, 2] - 16])
+        effLen = np.zeros((Ng, 6), np.float32)
+        effLen[:, 0], effLen[:, 2], effLen[:, 4], effLen[:, 5] = L[0], L[2], L[1], L[2]
+        eff3 = np.ones((3, ld), np.float32)
+        eff3[:, :Ng] = L
+    else:
+        effLen, eff3 = None, None
+    cdr = rng.beta(1.2, 5.0, Ng)
+    lam = np.exp(rng.normal(1.0, 1.0, Ng))
+    dev = torch.device(device)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+    d_mean, d_sd, d_lam, d_cdr = t(pad(b)), t(pad(sig, 1.0)), t(pad(lam)), t(pad(cdr))
+    wc_pad = np.zeros((max(Kc, 1), ld), np.float32)
+    wc_pad[:Kc, :Ng] = Wc
+    d_Wc, d_Xc = t(wc_pad), t(Xc if Kc > 0 else np.zeros((Nc, 1), np.float32))
+    d_eff = t(eff3) if eff3 is not None else None
+    outs = [torch.empty((Nc, ld), dtype=torch.float32, device=dev) for _ in range(n_layers)]
+    with torch.cuda.device(dev):
+        _lib.check(lib.brie_simulate_counts(
+            seed, Nc, Ng, ld, event_offset, d_mean.data_ptr(), d_sd.data_ptr(), d_Xc.data_ptr(), d_Wc.data_ptr(), Kc,
+            d_eff.data_ptr() if d_eff is not None else None, d_lam.data_ptr(), d_cdr.data_ptr(),
+            C.c_float(pseudo_count), outs[0].data_ptr(), outs[1].data_ptr(),
+            outs[2].data_ptr() if n_layers > 2 else None, C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+    return dict(layers=outs, ld=ld, effLen=effLen, Xc=Xc,
+                truth=dict(Wc=Wc.astype(np.float32), b=b.astype(np.float32), sigma=sig.astype(np.float32),
+                           cdr=cdr, lam=lam))

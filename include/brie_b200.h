@@ -160,13 +160,16 @@ int brie_philox_normals_device(uint64_t seed, uint32_t phase, uint32_t model, ui
                                float* out, void* stream);
 
 /* Synthetic counts on the device, following brie/models/simulator.py:54-73 and
- * simulator/simuPSI.py:129-130 (bench.py workloads too large for host RAM).
- * psi (Nc, ld) in; per-event L (3, ld), rate lam (ld), detection prob cdr (ld). */
+ * simulator/simuPSI.py:129-130 (bench.py workloads too large for host RAM):
+ * z = logit_mean[g] + Xc[c,:] Wc[:,g] + logit_sd[g] N(0,1) clipped to +-9, psi = sigmoid(z),
+ * n ~ Poisson(lam[g]) Bernoulli(cdr[g]), (c1,c2,c3) ~ Multinomial(n, [psi L1, (1-psi) L2, L3] / sum),
+ * then the pseudo-count of model_wrap.py:113-117.  Per-event vectors have ld entries, Wc is
+ * (Kc, ld), efflen3 (3, ld) or NULL (L = 1,1,0), c3 may be NULL; outputs are (n_cells, ld). */
 int brie_simulate_counts(uint64_t seed, int64_t n_cells, int64_t n_events, int64_t ld,
-                         int64_t event_offset, const float* logit_mean /* (ld) */,
-                         const float* logit_sd /* (ld) */, const float* Xc, const float* Wc,
-                         int32_t Kc, const float* efflen3, const float* lam, const float* cdr,
-                         float pseudo_count, float* c1, float* c2, float* c3, void* stream);
+                         int64_t event_offset, const float* logit_mean, const float* logit_sd,
+                         const float* Xc, const float* Wc, int32_t Kc, const float* efflen3,
+                         const float* lam, const float* cdr, float pseudo_count, float* c1, float* c2,
+                         float* c3, void* stream);
 
 #ifdef __cplusplus
 }
