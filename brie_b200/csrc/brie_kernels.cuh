@@ -634,68 +634,119 @@ struct EvalArgs {
   int32_t model_id[kMaxModels];
 };
 
+// One element with reads: its n_eval evaluations are spread over the 32 lanes (lane takes
+// evaluations lane, lane+32, ...), so lane utilisation does not depend on the sparsity pattern;
+// the warp sum is a fixed xor-shuffle tree (deterministic).  Returns sum over all samples of
+// c1 log psi + c2 log(1-psi) - n log D  (without the constant sum_k c_k log L_k).
+__device__ __forceinline__ float eval_item(float mu, float s, float c1, float c2, float n, float L1, float L2,
+                                           float L3, bool eff, int n_eval, int S, uint32_t event, uint32_t cell,
+                                           uint32_t stream0, uint64_t seed, int lane) {
+  float acc = 0.f;
+  for (int it = lane; it < n_eval; it += 32) {
+    for (int s0 = 0; s0 < S; s0 += 4) {
+      float eps[4];
+      brie_normals4(event, cell, (uint32_t)it, stream0 + (uint32_t)(s0 >> 2), seed, eps);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (s0 + q < S) {
+          const float z = fmaf(s, eps[q], mu);
+          const float e = expf(-fabsf(z));
+          const float lsp = fminf(z, 0.f) - log1pf(e);
+          const float inv = 1.0f / (1.0f + e);
+          const float psi = z >= 0.f ? inv : e * inv;
+          const float qq = z >= 0.f ? e * inv : inv;
+          const float D = fmaf(psi, L1, fmaf(qq, L2, L3));
+          acc += fmaf(c1, lsp, c2 * (lsp - z)) - (eff ? n * logf(D) : 0.f);
+        }
+      }
+    }
+  }
+  return warp_sum(acc);
+}
+
 __global__ void __launch_bounds__(kThreads) eval_loss_kernel(const EvalArgs a) {
   const int m = blockIdx.x, tile = blockIdx.y, chunk = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t g = (int64_t)tile * kTileCols + lane;  // lane-strided columns: g, g+32, g+64, g+96
+  const int64_t g0 = (int64_t)tile * kTileCols + lane * 4;
+  const bool in_ld = g0 < a.ld;
   float kl[4] = {0.f, 0.f, 0.f, 0.f}, ll[4] = {0.f, 0.f, 0.f, 0.f};
   const int64_t row_begin = (int64_t)chunk * a.rows_per_cta;
   const int64_t row_end = min(row_begin + (int64_t)a.rows_per_cta, a.Nc);
   const int64_t plane = a.Nc * a.ld;
   const uint32_t stream0 = brie_stream_word(BRIE_PHASE_EVAL, (uint32_t)a.model_id[m], 0u);
   const float inv_n = 1.0f / ((float)a.n_eval * (float)a.S);
-  for (int j = 0; j < 4; ++j) {
-    const int64_t gj = g + 32 * j;
-    if (gj >= a.Ng) continue;
-    float L1 = 1.f, L2 = 1.f, L3 = 0.f;
-    if (a.eff) { L1 = a.eff[gj]; L2 = a.eff[a.ld + gj]; L3 = a.eff[2 * a.ld + gj]; }
-    const float lL1 = logf(L1), lL2 = logf(L2), lL3 = a.eff ? logf(L3) : 0.f;
-    float b = 0.f, tau = 0.f;
-    if (!a.cell_mode) { b = a.b[(int64_t)m * a.ld + gj]; tau = a.tau[(int64_t)m * a.ld + gj]; }
-    for (int64_t row = row_begin + warp; row < row_end; row += kWarps) {
-      const int64_t off = row * a.ld + gj;
-      const float mu = a.Zl[(int64_t)m * plane + off], lam = a.Zs[(int64_t)m * plane + off];
-      if (a.cell_mode) { b = a.b[(int64_t)m * a.Nc + row]; tau = a.tau[(int64_t)m * a.Nc + row]; }
-      float pm = b;
-      for (int k = 0; k < a.KC; ++k)
-        pm = fmaf(a.Xc[row * a.KC + k], a.Wc[((int64_t)m * a.KC + k) * a.ld + gj], pm);
-      for (int k = 0; k < a.KG; ++k)
-        pm = fmaf(a.Wg[((int64_t)m * a.Nc + row) * a.KG + k], a.Xg[gj * a.KG + k], pm);
-      const float d = lam - tau;
-      const float r0 = (mu - pm) * expf(-tau);
-      kl[j] += 0.5f * r0 * r0 + 0.5f * expm1f(2.0f * d) - d;
-      const float c1 = a.c[0][off], c2 = a.c[1][off], c3 = a.c[2] ? a.c[2][off] : 0.f;
-      const float n = c1 + c2 + c3;
-      if (n > 0.f) {
-        const float s = expf(lam);
-        float acc = 0.f;
-        for (int it = 0; it < a.n_eval; ++it) {
-          for (int s0 = 0; s0 < a.S; s0 += 4) {
-            float eps[4];
-            brie_normals4((uint32_t)(a.event_offset + gj), (uint32_t)row, (uint32_t)it,
-                          stream0 + (uint32_t)(s0 >> 2), a.seed, eps);
+  const bool eff = a.eff != nullptr;
+  float L1[4], L2[4], L3[4], bb[4], tau[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              if (s0 + q < a.S) {
-                const float z = fmaf(s, eps[q], mu);
-                const float e = expf(-fabsf(z));
-                const float lsp = fminf(z, 0.f) - log1pf(e);
-                const float inv = 1.0f / (1.0f + e);
-                const float psi = z >= 0.f ? inv : e * inv;
-                const float qq = z >= 0.f ? e * inv : inv;
-                const float D = fmaf(psi, L1, fmaf(qq, L2, L3));
-                acc += fmaf(c1, lsp, c2 * (lsp - z)) - (a.eff ? n * logf(D) : 0.f);
-              }
-            }
-          }
+  for (int j = 0; j < 4; ++j) {
+    const int64_t gj = g0 + j;
+    L1[j] = 1.f; L2[j] = 1.f; L3[j] = 0.f; bb[j] = 0.f; tau[j] = 0.f;
+    if (gj < a.ld) {
+      if (eff) { L1[j] = a.eff[gj]; L2[j] = a.eff[a.ld + gj]; L3[j] = a.eff[2 * a.ld + gj]; }
+      if (!a.cell_mode) { bb[j] = a.b[(int64_t)m * a.ld + gj]; tau[j] = a.tau[(int64_t)m * a.ld + gj]; }
+    }
+  }
+  for (int64_t row = row_begin + warp; row < row_end; row += kWarps) {
+    float mu[4] = {0.f, 0.f, 0.f, 0.f}, lam[4] = {0.f, 0.f, 0.f, 0.f};
+    float c1[4] = {0.f, 0.f, 0.f, 0.f}, c2[4] = {0.f, 0.f, 0.f, 0.f}, c3[4] = {0.f, 0.f, 0.f, 0.f};
+    if (in_ld) {
+      const int64_t off = row * a.ld + g0;
+      const float4 t0 = *reinterpret_cast<const float4*>(a.Zl + (int64_t)m * plane + off);
+      const float4 t1 = *reinterpret_cast<const float4*>(a.Zs + (int64_t)m * plane + off);
+      const float4 t2 = *reinterpret_cast<const float4*>(a.c[0] + off);
+      const float4 t3 = *reinterpret_cast<const float4*>(a.c[1] + off);
+      mu[0] = t0.x; mu[1] = t0.y; mu[2] = t0.z; mu[3] = t0.w;
+      lam[0] = t1.x; lam[1] = t1.y; lam[2] = t1.z; lam[3] = t1.w;
+      c1[0] = t2.x; c1[1] = t2.y; c1[2] = t2.z; c1[3] = t2.w;
+      c2[0] = t3.x; c2[1] = t3.y; c2[2] = t3.z; c2[3] = t3.w;
+      if (a.c[2]) {
+        const float4 t4 = *reinterpret_cast<const float4*>(a.c[2] + off);
+        c3[0] = t4.x; c3[1] = t4.y; c3[2] = t4.z; c3[3] = t4.w;
+      }
+    }
+    float b_row = 0.f, tau_row = 0.f;
+    if (a.cell_mode) { b_row = a.b[(int64_t)m * a.Nc + row]; tau_row = a.tau[(int64_t)m * a.Nc + row]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t gj = g0 + j;
+      const bool valid = gj < a.Ng;
+      float n = 0.f;
+      if (valid) {
+        const float tj = a.cell_mode ? tau_row : tau[j];
+        float pm = a.cell_mode ? b_row : bb[j];
+        for (int k = 0; k < a.KC; ++k)
+          pm = fmaf(a.Xc[row * a.KC + k], a.Wc[((int64_t)m * a.KC + k) * a.ld + gj], pm);
+        for (int k = 0; k < a.KG; ++k)
+          pm = fmaf(a.Wg[((int64_t)m * a.Nc + row) * a.KG + k], a.Xg[gj * a.KG + k], pm);
+        const float d = lam[j] - tj;
+        const float r0 = (mu[j] - pm) * expf(-tj);
+        kl[j] += 0.5f * r0 * r0 + 0.5f * expm1f(2.0f * d) - d;
+        n = c1[j] + c2[j] + c3[j];
+      }
+      // elements with reads, one at a time, all 32 lanes cooperating
+      uint32_t todo = __ballot_sync(0xffffffffu, n > 0.f);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float imu = __shfl_sync(0xffffffffu, mu[j], src), ilam = __shfl_sync(0xffffffffu, lam[j], src);
+        const float ic1 = __shfl_sync(0xffffffffu, c1[j], src), ic2 = __shfl_sync(0xffffffffu, c2[j], src);
+        const float in = __shfl_sync(0xffffffffu, n, src);
+        const float l1 = __shfl_sync(0xffffffffu, L1[j], src), l2 = __shfl_sync(0xffffffffu, L2[j], src);
+        const float l3 = __shfl_sync(0xffffffffu, L3[j], src);
+        const uint32_t ev = (uint32_t)(a.event_offset + (int64_t)tile * kTileCols + src * 4 + j);
+        const float tot = eval_item(imu, expf(ilam), ic1, ic2, in, l1, l2, l3, eff, a.n_eval, a.S, ev, (uint32_t)row,
+                                    stream0, a.seed, lane);
+        if (lane == src) {
+          const float k0 = eff ? fmaf(c1[j], logf(L1[j]), fmaf(c2[j], logf(L2[j]), c3[j] * logf(L3[j]))) : 0.f;
+          ll[j] += fmaf(tot, inv_n, k0);
         }
-        ll[j] += fmaf(acc, inv_n, fmaf(c1, lL1, fmaf(c2, lL2, c3 * lL3)));
       }
     }
   }
   __shared__ float red[kWarps][kTileCols];
   for (int i = 0; i < 2; ++i) {
-    for (int j = 0; j < 4; ++j) red[warp][lane + 32 * j] = i == 0 ? kl[j] : ll[j];
+    *reinterpret_cast<float4*>(&red[warp][lane * 4]) =
+        i == 0 ? make_float4(kl[0], kl[1], kl[2], kl[3]) : make_float4(ll[0], ll[1], ll[2], ll[3]);
     __syncthreads();
     const int64_t gcol = (int64_t)tile * kTileCols + threadIdx.x;
     if (threadIdx.x < kTileCols && gcol < a.ld) {
