@@ -11,6 +11,7 @@ import numpy as np
 from scipy.stats import chi2
 
 from ..engine import FitEngine
+from ..sharding import event_shards
 from ..settings import verbosity
 
 
@@ -220,11 +221,55 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
             brie_results.cell_coeff = np.append(brie_results.cell_coeff, wc_last, axis=0)  # :186-187
     brie_results.ELBO_gain = ELBO_gain                              # H1 vs NUll
     brie_results.pval = chi2.sf(2 * ELBO_gain, df=1)                # :190
+    # The reference corrects for multiple testing inside each fit_BRIE_matrix call, i.e. per event
+    # batch when called from fitBRIE (:193-196 under :245-256): keep that scope per convergence group.
     fdr = np.zeros(ELBO_gain.shape)
-    for i in range(fdr.shape[1]):
-        fdr[:, i] = fdr_bh(brie_results.pval[:, i])                 # :193-196
+    if group_size is None:
+        bounds = [(0, Ng)]
+    else:
+        first = event_offset // group_size
+        last = (event_offset + Ng - 1) // group_size
+        bounds = [(max(g * group_size - event_offset, 0), min((g + 1) * group_size - event_offset, Ng))
+                  for g in range(first, last + 1)]
+    for lo, hi in bounds:
+        for i in range(fdr.shape[1]):
+            fdr[lo:hi, i] = fdr_bh(brie_results.pval[lo:hi, i])
     brie_results.fdr = fdr
     return brie_results
+
+
+def _dist_info():
+    """(torch.distributed, rank, world) -- world 1 when no process group is initialised."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist, dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return None, 0, 1
+
+
+def _merge_shared(parts):
+    """Merge event shards of ONE fit whose per-cell parameters and loss trace are shared (identical
+    on every rank after the all-reduce): only per-event fields are concatenated."""
+    out = parts[0]
+    for r in parts[1:]:
+        out.Ng += r.Ng
+        out.loss_gene = np.append(out.loss_gene, r.loss_gene)
+        out.cell_coeff = np.append(out.cell_coeff, r.cell_coeff, axis=1)
+        for k in ('Psi', 'Psi95CI', 'Z_std', 'Z_loc'):
+            setattr(out, k, np.append(getattr(out, k), getattr(r, k), axis=1))
+        if out.intercept_mode.upper() != 'CELL':
+            out.sigma = np.append(out.sigma, r.sigma, axis=1)
+            out.intercept = np.append(out.intercept, r.intercept, axis=1)
+        if hasattr(r, 'ELBO_gain'):
+            for k in ('fdr', 'pval', 'ELBO_gain'):
+                setattr(out, k, np.append(getattr(out, k), getattr(r, k), axis=0))
+    out.shape = (out.Nc, out.Ng)
+    if hasattr(out, 'pval'):               # one fit => one multiple-testing scope over all events
+        for i in range(out.fdr.shape[1]):
+            out.fdr[:, i] = fdr_bh(out.pval[:, i])
+    return out
 
 
 def _device_event_budget(Nc, n_models, n_layers, device=None, frac=0.7):
@@ -255,16 +300,18 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
     Nc, Ng = adata.shape
     n_models = 1 + len(LRT_index)
 
+    dist, rank, world = _dist_info()
     if (Xg is None or Xg.shape[1] == 0) and intercept_mode.upper() != 'CELL':   # :241
         # Events are independent here; the reference fits them in sequential batches of
-        # _n_gene events (:242-258).  We keep _n_gene as the convergence group and fit as many
-        # groups per launch as HBM holds.
+        # _n_gene events (:242-258).  We keep _n_gene as the convergence group, fit as many
+        # groups per launch as HBM holds, and give each GPU a contiguous range of groups.
         _n_gene = int(np.ceil(batch_size / Nc))
         chunk = _device_event_budget(Nc, n_models, len(layer_keys), keyargs.get('device'))
         chunk = max(chunk // _n_gene, 1) * _n_gene
+        lo, hi = event_shards(Ng, world, _n_gene)[rank]
         res_list = []
-        for e0 in range(0, Ng, chunk):
-            _idx = range(e0, min(e0 + chunk, Ng))
+        for e0 in range(lo, hi, chunk):
+            _idx = range(e0, min(e0 + chunk, hi))
             _count_layers = [adata.layers[_key][:, _idx] for _key in layer_keys]
             _effLen = adata.varm['effLen'][_idx, :] if 'effLen' in adata.varm else None
             _ResVal = fit_BRIE_matrix(
@@ -274,8 +321,27 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
                 base_mode=base_mode, tau_prior=tau_prior, group_size=_n_gene,
                 event_offset=e0, n_events_total=Ng, **keyargs)
             res_list.append(_ResVal)
-            print("[BRIE2] %d out %d genes done" % (min(e0 + chunk, Ng), Ng))
+            print("[BRIE2] %d out %d genes done" % (min(e0 + chunk, hi) - lo, hi - lo))
+        if world > 1:                      # every rank ends up with the full result, in event order
+            parts = [None] * world
+            dist.all_gather_object(parts, res_list)
+            res_list = [r for p in parts for r in p]
         ResVal = concate(res_list)
+    elif world > 1:
+        # shared per-cell parameters: shard events, all-reduce the shared gradients (engine.py)
+        lo, hi = event_shards(Ng, world, 1)[rank]
+        _idx = range(lo, hi)
+        _count_layers = [adata.layers[_key][:, _idx] for _key in layer_keys]
+        _effLen = adata.varm['effLen'][_idx, :] if 'effLen' in adata.varm else None
+        local = fit_BRIE_matrix(
+            _count_layers, Xc=Xc, Xg=Xg[_idx, :], effLen=_effLen, intercept=intercept,
+            intercept_mode=intercept_mode, LRT_index=LRT_index,
+            pseudo_count=pseudo_count, sigma=sigma, base_mode=base_mode,
+            tau_prior=tau_prior, event_offset=lo, n_events_total=Ng,
+            dist_group=dist.group.WORLD, **keyargs)
+        parts = [None] * world
+        dist.all_gather_object(parts, local)
+        ResVal = _merge_shared(parts)
     else:                                                           # :261-269
         _count_layers = [adata.layers[_key] for _key in layer_keys]
         _effLen = adata.varm['effLen'] if 'effLen' in adata.varm else None

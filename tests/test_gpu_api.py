@@ -53,7 +53,8 @@ def test_fitBRIE_groups_match_sequential_reference_batches():
     assert len(set(res.n_iter.reshape(-1).tolist())) > 1, "want groups that stop at different times"
     Psi = np.concatenate([r.Psi for r in refs], axis=1)
     gain = np.concatenate([r.ELBO_gain for r in refs], axis=0)
-    fdr_in = np.concatenate([r.pval for r in refs], axis=0)
+    fdr = np.concatenate([r.fdr for r in refs], axis=0)              # BH per batch, as the reference
+    assert np.array_equal(res.fdr < 0.05, fdr < 0.05) and np.abs(res.fdr - fdr).max() < 5e-3
     assert np.quantile(np.abs(res.Psi - Psi), 0.99) < 1e-3
     big = np.abs(gain) > 1.5
     assert (np.abs(res.ELBO_gain - gain)[big] / np.abs(gain)[big]).max() < 1e-3
