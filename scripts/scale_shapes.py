@@ -60,7 +60,10 @@ def run(name, steps=30, warm=5, loss=False):
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or ["C2", "C3", "C4", "C5"]
-    for n in names:
-        run(n)
-        run(n, loss=True)
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    only = [a for a in sys.argv[1:] if a.startswith("--")]        # --loss / --noloss: one variant only (ncu runs)
+    for n in args or ["C2", "C3", "C4", "C5"]:
+        if "--loss" not in only:
+            run(n)
+        if "--noloss" not in only:
+            run(n, loss=True)
