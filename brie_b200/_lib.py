@@ -69,6 +69,12 @@ SYMBOLS = {
                                              C.c_int64, C.c_int64, C.c_int64, _P, _P]),
     "brie_simulate_counts": (C.c_int, [C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P,
                                        C.c_int32, _P, _P, _P, C.c_float, _P, _P, _P, _P]),
+    "brie_ingest_csc": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
+    "brie_ingest_csr": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int64, _P, _P, _P, _P, _P]),
+    "brie_add_pseudo_count": (C.c_int, [C.c_int64, C.c_int64, C.c_float, _P, _P, _P]),
+    "brie_gene_stats_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
+    "brie_gene_stats": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P]),
+    "brie_gather_events": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_int64, C.c_int64, _P, _P]),
 }
 
 _lib = None

@@ -50,9 +50,11 @@ def quant(in_file, cell_file=None, gene_file=None, out_file=None,
         adata = adata[mm1, :]
 
     print("layers:", layer_keys)                                 # quant.py:69-75
+    import torch
     adata = filter_genes(adata, min_counts=min_counts, min_counts_uniq=min_counts_uniq,
                          min_cells_uniq=min_cells_uniq, min_MIF_uniq=min_MIF_uniq,
-                         uniq_layers=layer_keys[:2], ambg_layers=layer_keys[2:], copy=True)
+                         uniq_layers=layer_keys[:2], ambg_layers=layer_keys[2:], copy=True,
+                         device="cuda" if torch.cuda.is_available() else None)
 
     Xg, Xg_ids = None, None
     if gene_file is not None:                                    # quant.py:78-98

@@ -14,10 +14,13 @@
 #include "../../include/brie_b200.h"
 #include "brie_kernels.cuh"
 
+#include "brie_host.h"
+
 namespace {
-
 thread_local std::string g_err;
+}
 
+namespace brie {
 int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -27,18 +30,7 @@ int fail(int code, const char* fmt, ...) {
   g_err = buf;
   return code;
 }
-
-#define BRIE_CUDA(call)                                                                  \
-  do {                                                                                   \
-    cudaError_t e_ = (call);                                                             \
-    if (e_ != cudaSuccess)                                                               \
-      return fail(BRIE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
-                  __FILE__, __LINE__);                                                   \
-  } while (0)
-
-int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
-
-}  // namespace
+}  // namespace brie
 
 struct brie_fit {
   brie_fit_desc d;
@@ -105,13 +97,6 @@ cudaError_t dispatch_step(const StepArgs& a, int KC, int KG, bool cell, bool los
     case 8: return dispatch_step1<8>(a, KG, cell, loss, grid, s);
   }
   return cudaErrorInvalidValue;
-}
-
-int grid_1d(int64_t n, int block) {
-  int64_t g = ceil_div(n, block);
-  if (g > 148 * 32) g = 148 * 32;
-  if (g < 1) g = 1;
-  return (int)g;
 }
 
 // bit m set iff model m still has an active event.  In shared-parameter fits

@@ -12,6 +12,7 @@ from scipy.stats import chi2
 
 from ..engine import FitEngine
 from ..sharding import event_shards
+from ..utils.layer_store import LayerStore
 from ..settings import verbosity
 
 
@@ -137,16 +138,33 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     for k in ('target', 'optimizer', 'learn_rate', 'verbose'):      # accepted and ignored (:214-237)
         keyargs.pop(k, None)
 
-    for i in range(len(data)):                                      # :108-111
-        if issparse(data[i]):
-            data[i] = data[i].toarray().astype(np.float32)
-
-    print("[BRIE2] adding pseudo_count:", pseudo_count)             # :113-117 (in place, like the reference)
-    idx = data[0] + data[1] > 0
-    for i in range(2):
-        data[i][idx] = data[i][idx] + pseudo_count
-
+    import torch
+    from .. import ingest
+    if not torch.cuda.is_available():
+        raise RuntimeError("brie_b200: no CUDA device (there is no CPU fallback)")
+    dev = torch.device(device if device is not None else "cuda")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
     Nc, Ng = data[0].shape
+    print("[BRIE2] adding pseudo_count:", pseudo_count)
+    if any(issparse(d) or (torch.is_tensor(d) and d.is_cuda) for d in data):
+        # sparse layers are NOT densified on the host (:108-111): the stored counts go to the
+        # device, are scattered there and get the pseudo-count there (:113-117)
+        tiles, h2d_bytes = [], 0
+        for d in data:
+            t, nb = ingest.layer_to_device(d, 0, Ng, dev)
+            tiles.append(t)
+            h2d_bytes += nb
+        ingest.add_pseudo_count(tiles, pseudo_count)
+    else:
+        idx = data[0] + data[1] > 0                                 # :113-117 (in place, like the reference)
+        for i in range(2):
+            data[i][idx] = data[i][idx] + pseudo_count
+        tiles, h2d_bytes = [], 0
+        for d in data:
+            t, nb = ingest.layer_to_device(d, 0, Ng, dev)
+            tiles.append(t)
+            h2d_bytes += nb
     if Xc is None:
         Xc = np.ones((Nc, 0), np.float32)
     if Xg is None:
@@ -181,8 +199,9 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     trace_cap = max(int(keyargs.get('min_iter', 1000) / 6), int(keyargs.get('add_iter', 500)), 1)
     common = dict(effLen=effLen, Xc=Xc, Xg=Xg, intercept=intercept, sigma=sigma, MC_size=MC_size,
                   seed=seed, group_size=group_size, event_offset=event_offset,
-                  n_events_total=n_events_total, device=device, trace_cap=trace_cap,
-                  dist_group=dist_group)
+                  n_events_total=n_events_total, device=dev, trace_cap=trace_cap,
+                  dist_group=dist_group, n_events=Ng)
+    data = tiles
     cell_mode = intercept_mode.upper() == 'CELL'
     T = len(test_masks)
     # NB the reference builds the refits WITHOUT intercept_mode (model_wrap.py:174-178), so
@@ -205,7 +224,7 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     brie_results = _rv_from_engine(e0, m0, Xc[:, base_cols], Xg, intercept_mode)   # :146
     brie_results.n_iter = np.stack([engines[w[0]].n_iter[w[1]] for w in where], axis=0)  # (1+T, groups)
     brie_results.launch_count = sum(e.launch_count for e in engines)
-    brie_results.h2d_bytes = sum(e.h2d_bytes for e in engines)
+    brie_results.h2d_bytes = h2d_bytes
     if T == 0:                                                      # :152-153
         return brie_results
 
@@ -286,6 +305,10 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
             base_mode='full', tau_prior=[3, 27], **keyargs):
     """Fit a BRIE model from AnnData with cell and/or gene features (model_wrap.py:202-314).
 
+    `out_dir` (not in the reference): directory for `.npy` memory maps of the dense
+    (cells, events) outputs Psi / Psi95CI / Z_std / Z_loc, written event chunk by event chunk
+    (and rank by rank) -- for fits whose outputs exceed host RAM; default: RAM arrays.
+
     Returns the BRIE_RV result and adds to `adata` exactly the keys the reference adds
     (obsm['Xc'], varm['cell_coeff'], varm['Xg'], obsm['gene_coeff'], varm|obsm['intercept',
     'sigma'], layers['Psi','Z_std','Psi_95CI'], uns['brie_losses'], var['loss_gene'],
@@ -299,6 +322,7 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
         LRT_index = np.arange(Xc.shape[1])
     Nc, Ng = adata.shape
     n_models = 1 + len(LRT_index)
+    out_dir = keyargs.pop('out_dir', None)
 
     dist, rank, world = _dist_info()
     if (Xg is None or Xg.shape[1] == 0) and intercept_mode.upper() != 'CELL':   # :241
@@ -309,9 +333,12 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
         chunk = _device_event_budget(Nc, n_models, len(layer_keys), keyargs.get('device'))
         chunk = max(chunk // _n_gene, 1) * _n_gene
         lo, hi = event_shards(Ng, world, _n_gene)[rank]
+        # finished chunks go straight into their column range of the output arrays (RAM, or
+        # .npy memory maps under out_dir shared by all ranks) instead of np.append (:55-76)
+        store = LayerStore(Nc, Ng, out_dir, rank, world, dist)
         res_list = []
         for e0 in range(lo, hi, chunk):
-            _idx = range(e0, min(e0 + chunk, hi))
+            _idx = slice(e0, min(e0 + chunk, hi))
             _count_layers = [adata.layers[_key][:, _idx] for _key in layer_keys]
             _effLen = adata.varm['effLen'][_idx, :] if 'effLen' in adata.varm else None
             _ResVal = fit_BRIE_matrix(
@@ -320,13 +347,16 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
                 LRT_index=LRT_index, pseudo_count=pseudo_count, sigma=sigma,
                 base_mode=base_mode, tau_prior=tau_prior, group_size=_n_gene,
                 event_offset=e0, n_events_total=Ng, **keyargs)
+            store.put(e0, _ResVal)
             res_list.append(_ResVal)
             print("[BRIE2] %d out %d genes done" % (min(e0 + chunk, hi) - lo, hi - lo))
-        if world > 1:                      # every rank ends up with the full result, in event order
+        if world > 1:                      # per-event vectors: every rank gets all of them, in event order
             parts = [None] * world
             dist.all_gather_object(parts, res_list)
             res_list = [r for p in parts for r in p]
         ResVal = concate(res_list)
+        for k, v in store.finish().items():
+            setattr(ResVal, k, v)
     elif world > 1:
         # shared per-cell parameters: shard events, all-reduce the shared gradients (engine.py)
         lo, hi = event_shards(Ng, world, 1)[rank]

@@ -1,0 +1,72 @@
+"""Chunked writer for the dense (cells, events) outputs of a fit.
+
+The reference concatenates per-batch results with `np.append` (brie/models/model_wrap.py:
+55-76) and stores `layers['Psi','Z_std','Psi_95CI']` as dense arrays with the note
+"TODO: introduce sparse matrix for this" (:289-292): quadratic copying and, at atlas scale
+(1M x 20k: 80 GB per layer), more than host RAM.  Here the destination arrays are
+allocated once -- in RAM, or as `.npy` memory maps under `out_dir` -- and every finished
+event chunk is written into its column range.  With several ranks and an `out_dir` all
+ranks write their own event ranges into the same files (one node, one file system), so no
+(cells, events) array ever travels through a collective.
+"""
+import os
+
+import numpy as np
+
+BIG_KEYS = ('Psi', 'Psi95CI', 'Z_std', 'Z_loc')
+
+
+class LayerStore:
+    def __init__(self, n_cells, n_events, out_dir=None, rank=0, world=1, dist=None, keys=BIG_KEYS):
+        self.shape = (int(n_cells), int(n_events))
+        self.out_dir, self.rank, self.world, self.dist = out_dir, rank, world, dist
+        self.keys = tuple(keys)
+        self.ranges = []                    # event ranges this rank has written
+        self.arrays = {}
+        if out_dir is None:
+            for k in self.keys:
+                self.arrays[k] = np.empty(self.shape, np.float32)
+            return
+        os.makedirs(out_dir, exist_ok=True)
+        if rank == 0:
+            for k in self.keys:
+                m = np.lib.format.open_memmap(self.path(k), mode='w+', dtype=np.float32, shape=self.shape)
+                del m
+        self._barrier()
+        for k in self.keys:
+            self.arrays[k] = np.load(self.path(k), mmap_mode='r+')
+
+    def path(self, key):
+        return os.path.join(self.out_dir, "%s.npy" % key)
+
+    def _barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+
+    def put(self, e0, result):
+        """Move the big arrays of one chunk result into columns [e0, e0 + result.Ng) and leave
+        (cells, 0) stubs behind, so BRIE_RV.concate only appends the per-event vectors."""
+        e1 = e0 + result.Ng
+        for k in self.keys:
+            self.arrays[k][:, e0:e1] = getattr(result, k)
+            setattr(result, k, np.zeros((self.shape[0], 0), np.float32))
+        self.ranges.append((e0, e1))
+
+    def finish(self):
+        """Make every rank see all columns; returns {key: (cells, events) array}."""
+        if self.out_dir is not None:
+            for a in self.arrays.values():
+                a.flush()
+            self._barrier()
+            return {k: np.load(self.path(k), mmap_mode='r+') for k in self.keys}
+        if self.world > 1:
+            mine = [(e0, e1, {k: self.arrays[k][:, e0:e1] for k in self.keys}) for e0, e1 in self.ranges]
+            parts = [None] * self.world
+            self.dist.all_gather_object(parts, mine)
+            for r, p in enumerate(parts):
+                if r == self.rank:
+                    continue
+                for e0, e1, blk in p:
+                    for k in self.keys:
+                        self.arrays[k][:, e0:e1] = blk[k]
+        return self.arrays

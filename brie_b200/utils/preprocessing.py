@@ -26,27 +26,39 @@ def _col_stats(layers):
 
 def filter_genes(data, min_counts=0, min_cells=0, min_counts_uniq=0, min_cells_uniq=0,
                  min_MIF_uniq=0.001, uniq_layers=['isoform1', 'isoform2'],
-                 ambg_layers=['ambiguous'], copy=False):
+                 ambg_layers=['ambiguous'], copy=False, device=None):
     """Keep genes with enough total / unique counts, expressing cells and minor-isoform
-    frequency; adds `n_counts` and `n_counts_uniq` to `adata.var` (preprocessing.py:64-65)."""
+    frequency; adds `n_counts` and `n_counts_uniq` to `adata.var` (preprocessing.py:64-65).
+
+    `device` (not in the reference): a CUDA device -> the column statistics are computed by
+    libbrie_b200.so from the stored counts (brie_b200.ingest.filter_stats_device), event chunk
+    by event chunk; None -> host sparse arithmetic.  Both give identical masks."""
     from scipy.sparse import issparse
     adata = data.copy() if copy else data
     uniq = [adata.layers[k] for k in uniq_layers]
     ambg = [adata.layers[k] for k in ambg_layers]
-    u_sum, u_cells = _col_stats(uniq)
-    t_sum, t_cells = _col_stats(uniq + ambg)
 
-    def colsum(m):
-        return np.asarray(m.sum(0), dtype=np.float64).reshape(-1) if issparse(m) \
-            else np.asarray(m, dtype=np.float64).sum(0)
+    if device is not None:
+        from ..ingest import filter_stats_device
+        st = filter_stats_device(uniq, ambg, device)
+        s1, s2 = st['sum1'], st['sum2']
+        u_sum, u_cells = s1 + s2, st['cells_uniq']
+        t_sum, t_cells = u_sum + st['sum3'], st['cells_total']
+    else:
+        def colsum(m):
+            return np.asarray(m.sum(0), dtype=np.float64).reshape(-1) if issparse(m) \
+                else np.asarray(m, dtype=np.float64).sum(0)
+        u_sum, u_cells = _col_stats(uniq)
+        t_sum, t_cells = _col_stats(uniq + ambg)
+        s1, s2 = colsum(uniq[0]), colsum(uniq[1])
 
     keep = np.ones(adata.n_vars, dtype=bool)
     keep &= t_sum >= min_counts
     keep &= t_cells >= min_cells
     keep &= u_sum >= min_counts_uniq
     keep &= u_cells >= min_cells_uniq
-    keep &= colsum(uniq[0]) >= min_MIF_uniq * u_sum
-    keep &= colsum(uniq[1]) >= min_MIF_uniq * u_sum
+    keep &= s1 >= min_MIF_uniq * u_sum
+    keep &= s2 >= min_MIF_uniq * u_sum
 
     adata._inplace_subset_var(keep)
     adata.var['n_counts'] = t_sum[keep]

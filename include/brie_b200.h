@@ -171,6 +171,41 @@ int brie_simulate_counts(uint64_t seed, int64_t n_cells, int64_t n_events, int64
                          const float* lam, const float* cdr, float pseudo_count, float* c1, float* c2,
                          float* c3, void* stream);
 
+/* ---- count ingest in front of the fit --------------------------------------
+ * Replaces the host densification of sparse layers (`data[i].toarray()`,
+ * model_wrap.py:108-111; model_TFProb.py:135-137): scatter a CSC slab (events = columns,
+ * the format brie-count writes, io_utils.py:107) or a CSR matrix into the dense
+ * (n_cells, ld) float32 tile the fit reads.  `out` is zero-filled first; duplicate
+ * entries sum (as toarray() does); indices outside the tile are ignored.
+ *  csc: colptr has n_events + 1 entries relative to rows/vals (colptr[0] == 0 for a slab
+ *       cut out of a larger matrix), rows are cell ids.
+ *  csr: rowptr has n_cells + 1 entries, cols are GLOBAL event ids; the tile keeps
+ *       events [event_begin, event_begin + n_events).
+ * rows/cols/vals may be NULL for an empty layer. */
+int brie_ingest_csc(int64_t n_cells, int64_t n_events, int64_t ld, const int64_t* colptr,
+                    const int32_t* rows, const float* vals, float* out, void* stream);
+int brie_ingest_csr(int64_t n_cells, int64_t event_begin, int64_t n_events, int64_t ld,
+                    const int64_t* rowptr, const int32_t* cols, const float* vals, float* out,
+                    void* stream);
+
+/* Replaces the pseudo-count of model_wrap.py:113-117, in place on the device tiles:
+ * where c1 + c2 > 0 (float32), c1 += pseudo_count and c2 += pseudo_count. */
+int brie_add_pseudo_count(int64_t n_cells, int64_t ld, float pseudo_count, float* c1, float* c2,
+                          void* stream);
+
+/* Replaces the dense float64 accumulation of filter_genes (preprocessing.py:38-61): per event
+ * stats[0..2, g] = column sums of c1, c2, c3 (c3 may be NULL), stats[3, g] = number of cells
+ * with c1 + c2 > 0, stats[4, g] = number of cells with c1 + c2 + c3 > 0; all float64, (5, ld).
+ * `scratch` needs brie_gene_stats_scratch_bytes(n_cells, ld) bytes.  Deterministic. */
+size_t brie_gene_stats_scratch_bytes(int64_t n_cells, int64_t ld);
+int brie_gene_stats(int64_t n_cells, int64_t ld, const float* c1, const float* c2, const float* c3,
+                    double* stats, void* scratch, void* stream);
+
+/* Column gather of a dense tile (`adata._inplace_subset_var`, preprocessing.py:63, without a
+ * host round trip): out[r, j] = in[r, src[j]] for j < n_out, zero padding up to ld_out. */
+int brie_gather_events(int64_t n_cells, int64_t ld_in, const float* in, const int64_t* src,
+                       int64_t n_out, int64_t ld_out, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
