@@ -57,7 +57,7 @@ SYMBOLS = {
     "brie_fit_run_steps": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "brie_fit_step_phase": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "brie_fit_cell_grad": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
-    "brie_fit_eval_loss_gene": (C.c_int, [_P, C.c_int32, _P, _P]),
+    "brie_fit_eval_loss_gene": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     "brie_fit_posterior": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
     "brie_fit_group_trace": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
     "brie_fit_launch_count": (C.c_int64, [_P]),

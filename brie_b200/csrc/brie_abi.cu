@@ -258,8 +258,8 @@ int brie_fit_init_params(brie_fit* f, float intercept_const, float sigma_const, 
                                                       d.n_cells, d.ld, d.event_offset, 0, d.ld,
                                                       f->buf.Z_std_log + m * plane);
     f->launches += 2;
-    // Wc: the reference's refit deletes the tested column (model_wrap.py:161), so its Wc has one row
-    // per USED column; compact row kk of that matrix is the kk-th set bit of xc_mask.
+    // Wc: one row per column the model uses (the refits delete / append the tested column,
+    // model_wrap.py:161, 167); rows of padded columns stay 0.
     int kk = 0;
     for (int k = 0; k < d.Kc; ++k) {
       float* dst = f->buf.Wc + ((int64_t)m * d.Kc + k) * d.ld;
@@ -427,9 +427,10 @@ int brie_fit_cell_grad(brie_fit* f, float** ptr, int64_t* n_floats) {
   return BRIE_OK;
 }
 
-int brie_fit_eval_loss_gene(brie_fit* f, int32_t n_eval, float* loss_gene, void* stream) {
+int brie_fit_eval_loss_gene(brie_fit* f, int32_t n_eval, int32_t mc_size, float* loss_gene, void* stream) {
   if (!f || !f->bound || !loss_gene) return fail(BRIE_ERR_ARG, "null argument or fit not bound");
   if (n_eval < 1) return fail(BRIE_ERR_ARG, "n_eval must be >= 1");
+  if (mc_size < 1 || mc_size > 4096) return fail(BRIE_ERR_ARG, "mc_size out of range");
   cudaStream_t s = (cudaStream_t)stream;
   const brie_fit_desc& d = f->d;
   float* scratch = (float*)f->buf.scratch;
@@ -441,7 +442,7 @@ int brie_fit_eval_loss_gene(brie_fit* f, int32_t n_eval, float* loss_gene, void*
   a.Zl = f->buf.Z_loc; a.Zs = f->buf.Z_std_log;
   a.Wc = f->buf.Wc; a.b = f->buf.intercept; a.tau = f->buf.sigma_log; a.Wg = f->buf.Wg;
   a.part_ev = scratch + f->off_part_ev;
-  a.M = d.n_models; a.S = d.mc_size; a.n_eval = n_eval; a.rows_per_cta = f->sz.rows_per_cta;
+  a.M = d.n_models; a.S = mc_size; a.n_eval = n_eval; a.rows_per_cta = f->sz.rows_per_cta;
   a.KC = d.Kc; a.KG = d.Kg; a.cell_mode = d.cell_mode;
   for (int m = 0; m < d.n_models; ++m) a.model_id[m] = d.model_id[m];
   const dim3 grid(d.n_models, f->sz.n_col_tiles, f->sz.n_row_chunks);

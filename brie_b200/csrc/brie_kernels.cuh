@@ -43,7 +43,7 @@ struct StepArgs {
   uint64_t seed;
   const float* c[3];
   const float* eff;  // (3, ld) or null
-  const float* Xc;   // (Nc, KC)
+  const float* Xc;   // (M, Nc, KC): per-model design matrix (unused columns are zero)
   const float* Xg;   // (Ng, KG)
   float* Zl;         // (M, Nc, ld)
   float* Zs;
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   auto load_row_consts = [&](int64_t row) {
     const int64_t r = row < row_end ? row : row_end - 1;
 #pragma unroll
-    for (int k = 0; k < KC; ++k) xc_n[k] = __ldg(a.Xc + r * KC + k);
+    for (int k = 0; k < KC; ++k) xc_n[k] = __ldg(a.Xc + ((int64_t)m * a.Nc + r) * KC + k);
 #pragma unroll
     for (int k = 0; k < KG; ++k) wg_n[k] = __ldg(a.Wg + ((int64_t)m * a.Nc + r) * KG + k);
     if (CELL) {
@@ -715,7 +715,7 @@ __global__ void __launch_bounds__(kThreads) eval_loss_kernel(const EvalArgs a) {
         const float tj = a.cell_mode ? tau_row : tau[j];
         float pm = a.cell_mode ? b_row : bb[j];
         for (int k = 0; k < a.KC; ++k)
-          pm = fmaf(a.Xc[row * a.KC + k], a.Wc[((int64_t)m * a.KC + k) * a.ld + gj], pm);
+          pm = fmaf(a.Xc[((int64_t)m * a.Nc + row) * a.KC + k], a.Wc[((int64_t)m * a.KC + k) * a.ld + gj], pm);
         for (int k = 0; k < a.KG; ++k)
           pm = fmaf(a.Wg[((int64_t)m * a.Nc + row) * a.KG + k], a.Xg[gj * a.KG + k], pm);
         const float d = lam[j] - tj;

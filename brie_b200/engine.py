@@ -42,7 +42,10 @@ class FitEngine:
     effLen : (Ng, 6) array or None -- columns 0, 4, 5 are used (model_TFProb.py:176).
     Xc : (Nc, Kc) cell covariates (all columns any batched model uses).
     Xg : (Ng, Kg) gene features.
-    masks : list (one per model) of the Xc column indices that model uses.
+    masks : list (one per model) of the Xc column indices that model uses, in the order of
+        that model's own design matrix (np.delete / np.append of model_wrap.py:161, 167).
+        The device gets one compact (Nc, K) design matrix per model, K = the widest model --
+        a 15-covariate one-vs-rest LRT with --testBase null is 15 models of width <= 2.
     model_ids : RNG model word per model (default 0..M-1).
     intercept, sigma : None (trainable) or constants (model_TFProb.py:67-78).
     group_size : events per reference batch, ceil(batch_size / Nc) (model_wrap.py:242);
@@ -78,12 +81,12 @@ class FitEngine:
         Xc = np.zeros((Nc, 0), np.float32) if Xc is None else np.asarray(Xc, np.float32)
         Xg = np.zeros((Ng, 0), np.float32) if Xg is None else np.asarray(Xg, np.float32)
         self.Kc_real, self.Kg_real = Xc.shape[1], Xg.shape[1]
-        self.Kc = _pad_to(self.Kc_real, KC_SUPPORTED, "Kc")
-        self.Kg = _pad_to(self.Kg_real, KG_SUPPORTED, "Kg")
         if masks is None:
             masks = [list(range(self.Kc_real))]
         self.masks = [[int(k) for k in mk] for mk in masks]   # ordered: compact Wc row kk <-> column masks[m][kk]
         self.M = len(self.masks)
+        self.Kc = _pad_to(max(len(mk) for mk in self.masks), KC_SUPPORTED, "Kc (widest batched model)")
+        self.Kg = _pad_to(self.Kg_real, KG_SUPPORTED, "Kg")
         self.model_ids = list(range(self.M)) if model_ids is None else [int(i) for i in model_ids]
         self.shared = self.cell_mode or self.Kg_real > 0       # parameters shared across events
         if group_size is None or self.shared:
@@ -114,12 +117,13 @@ class FitEngine:
             self.eff = torch.from_numpy(eff).to(dev)
         else:
             self.eff = None
-        xc = np.zeros((self.Nc, max(self.Kc, 1)), np.float32)
-        xc[:, :self.Kc_real] = Xc
+        xc = np.zeros((self.M, self.Nc, max(self.Kc, 1)), np.float32)
+        for m, mk in enumerate(self.masks):
+            xc[m, :, :len(mk)] = Xc[:, mk]
         xg = np.zeros((self.Ng, max(self.Kg, 1)), np.float32)
         xg[:, :self.Kg_real] = Xg
         self.Xc_host, self.Xg_host = Xc, Xg
-        self.Xc = torch.from_numpy(xc[:, :max(self.Kc, 1)]).contiguous().to(dev)
+        self.Xc = torch.from_numpy(xc).to(dev)
         self.Xg = torch.from_numpy(xg[:, :max(self.Kg, 1)]).contiguous().to(dev)
 
         M = self.M
@@ -144,7 +148,7 @@ class FitEngine:
         d.trace_cap = self.trace_cap
         for m in range(M):
             d.model_id[m] = self.model_ids[m]
-            d.xc_mask[m] = sum(1 << k for k in self.masks[m])
+            d.xc_mask[m] = (1 << len(self.masks[m])) - 1
         self.desc = d
         h = C.c_void_p()
         _lib.check(self.lib.brie_fit_create(C.byref(d), C.byref(h)))
@@ -201,11 +205,6 @@ class FitEngine:
             ic = 0.0 if self.intercept_const is None else float(self.intercept_const)
             sc = 1.0 if self.sigma_const is None else float(self.sigma_const)
             _lib.check(self.lib.brie_fit_init_params(self.h, ic, sc, self._stream()))
-            for m, mk in enumerate(self.masks):
-                # the ABI fills compact rows in ascending column order; a refit that APPENDS its
-                # tested column (model_wrap.py:167) has that column as its last compact row
-                if mk != sorted(mk):
-                    self.Wc[m, mk] = self.Wc[m, sorted(mk)].clone()
             if init_objs is None:
                 return
             for m, ob in enumerate(init_objs):
@@ -218,8 +217,8 @@ class FitEngine:
                 else:
                     self.Z_std_log[m, :, :self.Ng] = f(np.log(np.asarray(ob.Z_std, np.float32)))
                 wc = np.asarray(ob.Wc_loc, np.float32).reshape(len(self.masks[m]), self.Ng)
-                for kk, k in enumerate(self.masks[m]):
-                    self.Wc[m, k, :self.Ng] = f(wc[kk])
+                if len(self.masks[m]):
+                    self.Wc[m, :len(self.masks[m]), :self.Ng] = f(wc)
                 if self.Kg_real > 0:
                     self.Wg[m, :, :self.Kg_real] = f(np.asarray(ob.Wg_loc).reshape(self.Nc, self.Kg_real))
                     self.Wg[m, :, self.Kg_real:] = 0
@@ -265,10 +264,13 @@ class FitEngine:
         ev[:, :self.Ng] = act[:, g]
         self.active.copy_(torch.from_numpy(ev).to(self.device))
 
-    def eval_loss_gene(self, n_eval=500):
+    def eval_loss_gene(self, n_eval=500, mc_size=1):
+        """Mean of n_eval per-event loss evaluations (model_TFProb.py:261-264); each evaluation
+        draws `mc_size` samples -- 1 in the reference, whose loop drops the fit's MC_size."""
         out = torch.zeros((self.M, self.ld), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.brie_fit_eval_loss_gene(self.h, int(n_eval), out.data_ptr(), self._stream()))
+            _lib.check(self.lib.brie_fit_eval_loss_gene(self.h, int(n_eval), int(mc_size), out.data_ptr(),
+                                                        self._stream()))
         return out[:, :self.Ng]
 
     def posterior(self, model=0):
@@ -332,8 +334,7 @@ class FitEngine:
         """Host copies in the reference's shapes for model m."""
         Ng = self.Ng
         out = {}
-        out['Wc_loc'] = self.Wc[m, self.masks[m], :Ng].cpu().numpy() if self.masks[m] \
-            else np.zeros((0, Ng), np.float32)
+        out['Wc_loc'] = self.Wc[m, :len(self.masks[m]), :Ng].cpu().numpy()
         out['Wg_loc'] = self.Wg[m, :, :self.Kg_real].cpu().numpy()
         if self.cell_mode:
             out['intercept'] = self.intercept[m, :self.Nc].cpu().numpy().reshape(self.Nc, 1)

@@ -236,7 +236,7 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
             ELBO_gain[:, ii] = lg_test - brie_results.loss_gene     # :183
         else:
             ELBO_gain[:, ii] = brie_results.loss_gene - lg_test     # :185
-            wc_last = et.Wc[mt, idx_k, :Ng].cpu().numpy()[None, :]
+            wc_last = et.Wc[mt, len(et.masks[mt]) - 1, :Ng].cpu().numpy()[None, :]
             brie_results.cell_coeff = np.append(brie_results.cell_coeff, wc_last, axis=0)  # :186-187
     brie_results.ELBO_gain = ELBO_gain                              # H1 vs NUll
     brie_results.pval = chi2.sf(2 * ELBO_gain, df=1)                # :190

@@ -13,8 +13,10 @@
  *    must hold zero counts.  Same layout as the reference's (Nc, Ng) tensors.
  *  - `n_models` independent models (the full/base fit plus the LRT refits of
  *    model_wrap.py:155-187) are batched in every launch; model-major arrays are
- *    (n_models, ...).  A refit "without covariate k" is the same design matrix
- *    with bit k cleared in `xc_mask[model]` (its Wc row stays 0).
+ *    (n_models, ...).  Every model has its own design matrix Xc[model] (Nc, Kc):
+ *    the columns that model uses (np.delete / np.append of model_wrap.py:161, 167),
+ *    in model order, zero-padded to the common width Kc; bit k of
+ *    `xc_mask[model]` says column k is in use (a padded column's Wc row stays 0).
  *  - The caller owns every buffer; the library allocates no persistent device
  *    memory.  Handles own small host structs only.
  *  - Every function returns 0 on success, <0 on error; brie_last_error() gives
@@ -49,7 +51,7 @@ typedef struct brie_fit_desc {
   int64_t event_offset;   /* global index of local event 0 (RNG counters) */
   uint64_t seed;          /* noise / init key */
   int32_t n_models;       /* 1 + number of LRT refits batched (model_wrap.py:156) */
-  int32_t Kc;             /* columns of Xc, 0..BRIE_MAX_KC (model_TFProb.py:48) */
+  int32_t Kc;             /* common (padded) width of the per-model Xc, 0..BRIE_MAX_KC (model_TFProb.py:48) */
   int32_t Kg;             /* columns of Xg, 0..BRIE_MAX_KG (model_TFProb.py:49) */
   int32_t mc_size;        /* MC_size (model_TFProb.py:130) */
   int32_t n_layers;       /* 2 or 3 count layers (model_TFProb.py:184) */
@@ -59,7 +61,7 @@ typedef struct brie_fit_desc {
   int32_t train_sigma;    /* sigma_log is a Variable (model_TFProb.py:73-78) */
   int32_t trace_cap;      /* slots in loss_trace per model */
   int32_t model_id[BRIE_MAX_MODELS]; /* RNG model word of each batched model */
-  uint32_t xc_mask[BRIE_MAX_MODELS]; /* bit k set: model uses Xc column k */
+  uint32_t xc_mask[BRIE_MAX_MODELS]; /* bit k set: column k of Xc[model] is a real covariate */
 } brie_fit_desc;
 
 typedef struct brie_fit_sizes {
@@ -75,7 +77,7 @@ typedef struct brie_fit_buffers {
   const float* counts[3]; /* (Nc, ld) isoform1, isoform2, ambiguous (NULL if n_layers == 2),
                              pseudo-count already applied (model_wrap.py:113-117) */
   const float* efflen3;   /* (3, ld): columns 0, 4, 5 of varm['effLen'] (model_TFProb.py:176); NULL if !has_efflen */
-  const float* Xc;        /* (Nc, Kc) row-major (model_TFProb.py:220) */
+  const float* Xc;        /* (M, Nc, Kc) row-major: per-model design matrices (model_TFProb.py:220) */
   const float* Xg;        /* (Ng, Kg) row-major (model_TFProb.py:221) */
   float* Z_loc;           /* (M, Nc, ld)  (model_TFProb.py:80) */
   float* Z_std_log;       /* (M, Nc, ld)  (model_TFProb.py:82) */
@@ -103,7 +105,7 @@ int brie_fit_get_sizes(const brie_fit* fit, brie_fit_sizes* out);
 int brie_fit_bind(brie_fit* fit, const brie_fit_buffers* buffers);
 
 /* Replaces Model_init (model_TFProb.py:12-31): Z_loc ~ N(0,1), Z_std_log ~ N(0,1),
- * Wc ~ N(0,1) on unmasked rows (compact row index as if masked rows were deleted),
+ * Wc ~ N(0,1) on rows in use (row index = position among the model's own columns),
  * Wg ~ N(0,1), intercept ~ N(0,1) if trained else `intercept_const`,
  * sigma_log = log(sigma_const) (1 -> 0).  Counter-based, see brie_philox.h. */
 int brie_fit_init_params(brie_fit* fit, float intercept_const, float sigma_const, void* stream);
@@ -128,8 +130,11 @@ int brie_fit_step_phase(brie_fit* fit, int32_t phase, int32_t trace_slot, void* 
 int brie_fit_cell_grad(brie_fit* fit, float** ptr, int64_t* n_floats);
 
 /* Replaces the 500x `get_loss(axis=0)` averaging (model_TFProb.py:261-264):
- * loss_gene[m, g] = sum_c KL - mean over n_eval*S fresh-noise samples of sum_c loglik. */
-int brie_fit_eval_loss_gene(brie_fit* fit, int32_t n_eval, float* loss_gene /* (M, ld) */, void* stream);
+ * loss_gene[m, g] = sum_c KL - mean over n_eval evaluations, each with `mc_size` fresh-noise
+ * samples, of sum_c loglik.  The reference's loop calls get_loss without the fit's **kwargs,
+ * so its evaluations use logLik_MC's default MC_size = 1 (model_TFProb.py:130), not --MCsize. */
+int brie_fit_eval_loss_gene(brie_fit* fit, int32_t n_eval, int32_t mc_size, float* loss_gene /* (M, ld) */,
+                            void* stream);
 
 /* Replaces the Psi / Psi95CI / Z_std properties (model_TFProb.py:88-106) for one model. */
 int brie_fit_posterior(brie_fit* fit, int32_t model, float* Psi, float* Psi95CI, float* Z_std,

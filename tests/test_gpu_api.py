@@ -198,3 +198,63 @@ def test_device_simulator_statistics_and_engine_zero_copy():
     eng.init_params(); eng.begin_stage(0.01); eng.run_steps(2, 0)
     torch.cuda.synchronize()
     assert np.isfinite(eng.loss_trace[0, 1, :Ng].cpu().numpy()).all()
+
+
+def test_fitBRIE_chunked_memmap_outputs_equal_single_chunk(tmp_path, monkeypatch):
+    """Event chunking (HBM budget) and the out_dir memory-mapped writer do not change results:
+    noise and init are keyed by global event ids, chunks are aligned to convergence groups."""
+    import brie_b200.models.model_wrap as mw
+    from brie_b200.models import fitBRIE
+    from brie_b200.utils.anndata_lite import AnnDataLite
+    from scipy.sparse import csc_matrix
+    Nc, Ng = 100, 90
+    data, effLen, Xc, _ = make_lrt_problem(Nc, Ng, seed=7)
+    kw = dict(Xc=Xc, LRT_index=None, intercept_mode='gene', batch_size=100 * 20, seed=4, min_iter=300, max_iter=800,
+              MC_size=2, n_eval=10)
+
+    def run(chunk_events, out_dir, sparse):
+        wrap = csc_matrix if sparse else (lambda x: x.copy())
+        ad = AnnDataLite(X=data[0] + data[1] + data[2],
+                         layers={'isoform1': wrap(data[0]), 'isoform2': wrap(data[1]), 'ambiguous': wrap(data[2])},
+                         varm={'effLen': effLen})
+        if chunk_events:
+            monkeypatch.setattr(mw, "_device_event_budget", lambda *a, **k: chunk_events)
+        else:
+            monkeypatch.undo()
+        return fitBRIE(ad, out_dir=out_dir, **kw), ad
+
+    r1, ad1 = run(None, None, False)
+    r2, ad2 = run(45, str(tmp_path / "layers"), True)          # 45 -> 40 events per chunk: chunks of 40, 40, 10
+    assert isinstance(ad2.layers['Psi'], np.memmap) and os.path.exists(str(tmp_path / "layers" / "Psi.npy"))
+    for k in ('Psi', 'Psi95CI', 'Z_std', 'Z_loc', 'loss_gene', 'ELBO_gain', 'pval', 'fdr', 'losses', 'cell_coeff',
+              'sigma', 'intercept', 'n_iter'):
+        assert np.array_equal(np.asarray(getattr(r1, k)), np.asarray(getattr(r2, k))), k
+    assert np.array_equal(np.asarray(ad1.layers['Psi_95CI']), np.asarray(ad2.layers['Psi_95CI']))
+
+
+def test_one_vs_rest_lrt_with_15_covariates_null_base():
+    """The reference's dentate-gyrus run (brie-tutorials/dentateGyrus/run_brie2.sh:31-36): 15 cell
+    covariates (detection rate + 14 cluster indicators), --testBase null, LRT on 1..14.  Each
+    batched model only carries its own columns (base: [0]; test ii: [0, idx]), so the device
+    design width is 2, not 15."""
+    from brie_b200.models import fit_BRIE_matrix
+    from brie_b200.engine import FitEngine
+    Nc, Ng, T = 120, 24, 14
+    rng = np.random.default_rng(3)
+    data, effLen, _, _ = make_problem(Nc, Ng, 0, 0, False, 2, seed=9)
+    cluster = rng.integers(0, T, Nc)
+    Xc = np.zeros((Nc, 1 + T), np.float32)
+    Xc[:, 0] = rng.uniform(0.05, 0.3, Nc)
+    Xc[np.arange(Nc), 1 + cluster] = 1
+    kw = dict(Xc=Xc, LRT_index=list(range(1, T + 1)), base_mode='null', intercept_mode='gene', min_iter=120,
+              max_iter=120, MC_size=2, n_eval=10)
+    res = fit_BRIE_matrix([x.copy() for x in data], seed=1, **kw)
+    assert res.ELBO_gain.shape == (Ng, T) and res.cell_coeff.shape == (1 + T, Ng) and res.n_iter.shape == (1 + T, 1)
+    ref = _patched_oracle(1, Nc, lambda: oracle_fit_matrix([x.copy() for x in data], dtype=np.float32, seed=1, **kw))
+    assert np.quantile(np.abs(res.Psi - ref.Psi), 0.99) < 1e-3
+    assert np.abs(res.cell_coeff - ref.cell_coeff).max() < 5e-3
+    assert np.abs(res.ELBO_gain - ref.ELBO_gain).max() < 2e-2
+    eng = FitEngine([x.copy() for x in data], Xc=Xc, masks=[[0]] + [[0, k] for k in range(1, T + 1)])
+    assert eng.Kc == 2 and eng.Xc.shape == (1 + T, Nc, 2)
+    with pytest.raises(ValueError, match="exceeds the supported maximum"):
+        FitEngine([x.copy() for x in data], Xc=np.ones((Nc, 40), np.float32))

@@ -150,19 +150,21 @@ def test_trajectory_parity(mode, eff, n_layers, Kc, Kg, intercept, sigma):
     assert np.abs(pr['sigma'] - om.sigma).max() < 2e-3
 
 
-def test_loss_gene_eval_parity():
+@pytest.mark.parametrize("S_eval", [1, 3])
+def test_loss_gene_eval_parity(S_eval):
+    """S_eval = 1 is what the reference's loss_gene loop uses (get_loss without **kwargs)."""
     Nc, Ng, S, seed, n_eval = 64, 77, 3, 2, 12
     data, effLen, Xc, Xg = make_problem(Nc, Ng, 1, 0, True, 3, seed=4)
     add_pseudo_count(data, np.float32(0.01))
     eng = _engine(data, effLen, Xc, None, MC_size=S, seed=seed, trace_cap=8)
     eng.init_params()
-    lg = eng.eval_loss_gene(n_eval)[0].cpu().numpy()
+    lg = eng.eval_loss_gene(n_eval, S_eval)[0].cpu().numpy()
     om = OracleBRIE2(Nc, Ng, 1, 0, effLen, None, 'gene', None, dtype=np.float64, seed=seed)
     om.Xc = Xc.astype(np.float64)
     epsf = device_eps_provider(seed, 0, Nc, Ng)
     ref = np.zeros(Ng)
     for it in range(n_eval):
-        ref += om.loss_and_grads(data, epsf(px.PHASE_EVAL, it, S), want_grads=False)[1]
+        ref += om.loss_and_grads(data, epsf(px.PHASE_EVAL, it, S_eval), want_grads=False)[1]
     ref /= n_eval
     assert np.abs(lg - ref).max() <= 2e-5 * np.abs(ref).max()
 

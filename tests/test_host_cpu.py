@@ -161,3 +161,60 @@ print("rank", r, "ok")
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+
+def test_layer_store_ram_and_memmap(tmp_path):
+    from brie_b200.utils.layer_store import LayerStore, BIG_KEYS
+    from brie_b200.models.model_wrap import BRIE_RV
+    rng = np.random.default_rng(0)
+    Nc, Ng = 9, 41
+    full = {k: rng.standard_normal((Nc, Ng)).astype(np.float32) for k in BIG_KEYS}
+    for out_dir in (None, str(tmp_path / "layers")):
+        st = LayerStore(Nc, Ng, out_dir)
+        for e0, e1 in [(0, 16), (16, 17), (17, 41)]:            # ragged chunks
+            rv = BRIE_RV()
+            rv.Nc, rv.Ng = Nc, e1 - e0
+            for k in BIG_KEYS:
+                setattr(rv, k, full[k][:, e0:e1].copy())
+            st.put(e0, rv)
+            assert rv.Psi.shape == (Nc, 0)                      # stub left behind for concate()
+        got = st.finish()
+        for k in BIG_KEYS:
+            assert np.array_equal(np.asarray(got[k]), full[k])
+        if out_dir:
+            assert np.array_equal(np.load(os.path.join(out_dir, "Psi.npy")), full['Psi'])
+
+
+def test_layer_store_two_process_gloo(tmp_path):
+    """world_size 2 (gloo): both ranks write their event ranges; RAM mode exchanges blocks,
+    memmap mode shares the files -- every rank ends with the full arrays."""
+    script = tmp_path / "w.py"
+    script.write_text('''
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch.distributed as dist
+from brie_b200.sharding import event_shards
+from brie_b200.utils.layer_store import LayerStore
+from brie_b200.models.model_wrap import BRIE_RV
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+Nc, Ng = 5, 37
+full = np.arange(Nc * Ng, dtype=np.float32).reshape(Nc, Ng)
+a, b = event_shards(Ng, w, 4)[r]
+for out_dir in (None, %r):
+    st = LayerStore(Nc, Ng, out_dir, r, w, dist, keys=("Psi",))
+    for e0 in range(a, b, 6):
+        rv = BRIE_RV(); rv.Nc = Nc; rv.Ng = min(e0 + 6, b) - e0
+        rv.Psi = full[:, e0:e0 + rv.Ng].copy()
+        st.put(e0, rv)
+    got = st.finish()
+    assert np.array_equal(np.asarray(got["Psi"]), full), (r, out_dir)
+dist.destroy_process_group()
+print("rank", r, "ok")
+''' % (ROOT, str(tmp_path / "shared")))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29633", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.count("ok") == 2
