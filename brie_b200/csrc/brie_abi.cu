@@ -39,6 +39,7 @@ struct brie_fit {
   bool bound = false;
   int nev_max = 0, ncell = 0;
   size_t off_part_ev = 0, off_part_cell = 0, off_G = 0;  // scratch carve-up (float offsets)
+  bool stage_open = false;   // begin_stage has set the learning rate and cleared the Adam moments
   float lr = 0.f;
   int64_t t = 0;             // Adam step within the current stage
   uint32_t global_step = 0;  // RNG step word: counts every optimisation step of the fit
@@ -155,7 +156,7 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
     return fail(BRIE_ERR_UNSUPPORTED, "grid too large (%lld row chunks, %d column tiles)", (long long)n_chunks,
                 n_tiles);
   }
-  f->nev_max = d.Kc + 2 + 2;
+  f->nev_max = d.Kc + 2 + 1;
   f->ncell = d.Kg + (d.cell_mode ? 2 : 0);
   f->sz.rows_per_cta = rows;
   f->sz.n_row_chunks = (int)n_chunks;
@@ -304,6 +305,7 @@ int brie_fit_begin_stage(brie_fit* f, float lr, void* stream) {
   const brie_fit_desc& d = f->d;
   BRIE_CUDA(cudaMemsetAsync(f->buf.adam_Z, 0, (size_t)4 * d.n_models * d.n_cells * d.ld * sizeof(float), s));
   BRIE_CUDA(cudaMemsetAsync(f->buf.adam_small, 0, f->sz.adam_small_floats * sizeof(float), s));
+  f->stage_open = true;
   f->lr = lr;
   f->t = 0;
   return BRIE_OK;
@@ -320,6 +322,7 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
   const uint32_t mmask = g_all_models(f);
   if (phase == 0) {
     if (f->step_open) return fail(BRIE_ERR_ARG, "phase 0 called twice");
+    if (!f->stage_open) return fail(BRIE_ERR_ARG, "brie_fit_begin_stage must be called before the first step");
     f->t += 1;
     const double t = (double)f->t;
     f->alpha = (float)((double)f->lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
@@ -346,14 +349,14 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
     if (timed) BRIE_CUDA(cudaEventRecord(f->ev1[f->ev_used++], s));
     f->launches += 1;
 
-    const int nev = d.Kc + (d.cell_mode ? 0 : 2) + (loss ? 2 : 0);
+    const int nev = d.Kc + (d.cell_mode ? 0 : 2) + (loss ? 1 : 0);
     if (nev > 0) {
       EventArgs e;
       memset(&e, 0, sizeof e);
       e.ld = d.ld; e.Ng = d.n_events; e.M = M; e.KC = d.Kc; e.NEV = nev; e.n_chunks = f->sz.n_row_chunks;
       e.idx_gb = d.cell_mode ? -1 : d.Kc;
       e.idx_gt = d.cell_mode ? -1 : d.Kc + 1;
-      e.idx_kl = loss ? d.Kc + (d.cell_mode ? 0 : 2) : -1;
+      e.idx_loss = loss ? d.Kc + (d.cell_mode ? 0 : 2) : -1;
       e.train_b = d.train_intercept; e.train_tau = d.train_sigma;
       e.trace_slot = trace_slot; e.trace_cap = d.trace_cap;
       e.alpha = f->alpha;

@@ -163,9 +163,8 @@ template <int KC, int KG, bool CELL, bool LOSS>
 struct StepTraits {
   static constexpr int kGB = KC;                       // index of d/d intercept (gene mode)
   static constexpr int kGT = KC + 1;                   // index of d/d sigma_log (gene mode)
-  static constexpr int kKL = KC + (CELL ? 0 : 2);      // KL sum
-  static constexpr int kLL = kKL + 1;                  // log-lik sum
-  static constexpr int NEV = KC + (CELL ? 0 : 2) + (LOSS ? 2 : 0);
+  static constexpr int kLoss = KC + (CELL ? 0 : 2);    // sum over cells of KL - loglik
+  static constexpr int NEV = KC + (CELL ? 0 : 2) + (LOSS ? 1 : 0);
   static constexpr int NCELL = KG + (CELL ? 2 : 0);
 };
 
@@ -343,7 +342,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     for (int i = 0; i < (NCELL > 0 ? NCELL : 1); ++i) cacc[i] = 0.f;
 
     // ---- phase A: KL terms, shared-parameter accumulators, non-zero detection ----
-    float gmu[4], glam[4], ll[4];
+    float gmu[4], glam[4];
     uint32_t nz = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -361,7 +360,6 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       const float q2 = diff * r;                         // ((mu - m) / sigma)^2
       gmu[j] = r;
       glam[j] = e2 - 1.0f;
-      ll[j] = 0.f;
       if (c1[j] + c2[j] + c3[j] > 0.f) nz |= 1u << j;
       const float gt = 1.0f - q2 - e2;                   // d loss / d sigma_log
 #pragma unroll
@@ -370,7 +368,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
         acc[T::kGB][j] -= r;
         acc[T::kGT][j] += gt;
       }
-      if (LOSS) acc[T::kKL][j] += 0.5f * q2 + 0.5f * (e2 - 1.0f) - d;  // TFP _kl_normal_normal
+      if (LOSS) acc[T::kLoss][j] += 0.5f * q2 + 0.5f * (e2 - 1.0f) - d;  // TFP _kl_normal_normal
       if (NCELL > 0 && (g0 + j) < a.Ng) {
 #pragma unroll
         for (int k = 0; k < KG; ++k) cacc[k] = fmaf(-xg[k][j], r, cacc[k]);
@@ -421,15 +419,11 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
         if ((nz >> j) & 1u) {
           gmu[j] -= q[2][pos];
           glam[j] -= q[3][pos];
-          if (LOSS) ll[j] = q[4][pos];
+          if (LOSS) acc[T::kLoss][j] -= q[4][pos];
           ++pos;
         }
       }
       __syncwarp();  // queue is reused by the next row
-    }
-    if (LOSS) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[T::kLL][j] += ll[j];
     }
 
     // ---- phase C: Adam on Z_loc / Z_std_log, clip, store ----
@@ -498,7 +492,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 struct EventArgs {
   int64_t ld, Ng;
   int32_t M, KC, NEV, n_chunks;
-  int32_t idx_gb, idx_gt, idx_kl;  // -1 if absent
+  int32_t idx_gb, idx_gt, idx_loss;  // -1 if absent
   int32_t train_b, train_tau, trace_slot, trace_cap;
   float alpha;
   const float* part_ev;
@@ -509,7 +503,7 @@ struct EventArgs {
   uint32_t xc_mask[kMaxModels];
 };
 
-constexpr int kMaxNEV = 12;  // BRIE_MAX_KC + 2 + 2
+constexpr int kMaxNEV = 11;  // BRIE_MAX_KC + 2 + 1
 
 // block = 8 warps x 32 events: warp w sums row chunks w, w+8, ... (coalesced 128-byte rows of the
 // partial buffer), warp 0 combines the 8 sub-sums in fixed order (f64) and applies the updates.
@@ -560,10 +554,8 @@ __global__ void __launch_bounds__(256) event_update_kernel(const EventArgs a) {
     adam_update(x, mm, vv, grad, a.alpha);
     a.tau[pi] = x; a.mom[qi] = mm; a.mom[mstride + qi] = vv;
   }
-  if (a.idx_kl >= 0 && a.trace_slot >= 0) {
-    const double kl = red(a.idx_kl), ll = red(a.idx_kl + 1);
-    a.trace[((int64_t)m * a.trace_cap + a.trace_slot) * a.ld + g] = (float)(kl - ll);
-  }
+  if (a.idx_loss >= 0 && a.trace_slot >= 0)
+    a.trace[((int64_t)m * a.trace_cap + a.trace_slot) * a.ld + g] = (float)red(a.idx_loss);
 }
 
 // Per-cell gradient reduce over column tiles: G[m, c, i] = sum_tiles part_cell.
