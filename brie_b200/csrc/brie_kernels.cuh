@@ -382,7 +382,11 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     // ---- phase B: compacted Monte-Carlo work ----
     const uint32_t b0 = __ballot_sync(0xffffffffu, nz & 1u), b1 = __ballot_sync(0xffffffffu, nz & 2u);
     const uint32_t b2 = __ballot_sync(0xffffffffu, nz & 4u), b3 = __ballot_sync(0xffffffffu, nz & 8u);
+#ifdef BRIE_SKELETON   // measurement aid (scripts/ab.sh): memory skeleton only, no Monte-Carlo work
+    const int n_items = 0;
+#else
     const int n_items = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+#endif
     if (n_items > 0) {
       const int base = __popc(b0 & lt_mask) + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
       int pos = base;
