@@ -55,7 +55,7 @@ using namespace brie;
 
 namespace {
 
-bool kc_supported(int k) { return k == 0 || k == 1 || k == 2 || k == 4 || k == 8; }
+bool kc_supported(int k) { return k == 0 || k == 1 || k == 2 || k == 4 || k == 8 || k == 16; }
 bool kg_supported(int k) { return k == 0 || k == 4 || k == 8; }
 
 template <int KC, int KG, bool CELL, bool LOSS>
@@ -63,11 +63,11 @@ cudaError_t launch_step(const StepArgs& a, dim3 grid, cudaStream_t s) {
   static bool configured = false;  // per instantiation: opt in to > 48 KB dynamic shared memory
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(elbo_step_kernel<KC, KG, CELL, LOSS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kStepSmemBytes);
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, step_smem_bytes(KC));
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  elbo_step_kernel<KC, KG, CELL, LOSS><<<grid, kThreads, kStepSmemBytes, s>>>(a);
+  elbo_step_kernel<KC, KG, CELL, LOSS><<<grid, kThreads, step_smem_bytes(KC), s>>>(a);
   return cudaGetLastError();
 }
 
@@ -96,6 +96,7 @@ cudaError_t dispatch_step(const StepArgs& a, int KC, int KG, bool cell, bool los
     case 2: return dispatch_step1<2>(a, KG, cell, loss, grid, s);
     case 4: return dispatch_step1<4>(a, KG, cell, loss, grid, s);
     case 8: return dispatch_step1<8>(a, KG, cell, loss, grid, s);
+    case 16: return dispatch_step1<16>(a, KG, cell, loss, grid, s);   // 2 events per lane, 64-event tiles
   }
   return cudaErrorInvalidValue;
 }
@@ -125,7 +126,7 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
     return fail(BRIE_ERR_ARG, "cell / event index exceeds the 32-bit RNG counter words");
   if (d.n_models < 1 || d.n_models > BRIE_MAX_MODELS) return fail(BRIE_ERR_ARG, "n_models out of range");
   if (!kc_supported(d.Kc))
-    return fail(BRIE_ERR_UNSUPPORTED, "Kc must be one of 0,1,2,4,8 (pad Xc with zero columns)");
+    return fail(BRIE_ERR_UNSUPPORTED, "Kc must be one of 0,1,2,4,8,16 (pad Xc with zero columns)");
   if (!kg_supported(d.Kg))
     return fail(BRIE_ERR_UNSUPPORTED, "Kg must be one of 0,4,8 (pad Xg with zero columns)");
   if (d.mc_size < 1 || d.mc_size > 4096) return fail(BRIE_ERR_ARG, "mc_size out of range");
@@ -139,7 +140,7 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
   if (!f) return fail(BRIE_ERR_ARG, "out of host memory");
   f->d = d;
   memset(&f->buf, 0, sizeof f->buf);
-  const int n_tiles = (int)ceil_div(d.ld, kTileCols);
+  const int n_tiles = (int)ceil_div(d.ld, step_tile_cols(d.Kc));   // 128 events per tile, 64 when Kc = 16
   // rows per CTA: up to 256 (fewer row-chunk partials for event_update_kernel) while keeping
   // >= ~10 waves of 2 CTAs/SM (tail effect); small problems go down to one row per warp
   int rows = 256;
@@ -448,7 +449,7 @@ int brie_fit_eval_loss_gene(brie_fit* f, int32_t n_eval, int32_t mc_size, float*
   a.M = d.n_models; a.S = mc_size; a.n_eval = n_eval; a.rows_per_cta = f->sz.rows_per_cta;
   a.KC = d.Kc; a.KG = d.Kg; a.cell_mode = d.cell_mode;
   for (int m = 0; m < d.n_models; ++m) a.model_id[m] = d.model_id[m];
-  const dim3 grid(d.n_models, f->sz.n_col_tiles, f->sz.n_row_chunks);
+  const dim3 grid(d.n_models, (unsigned)ceil_div(d.ld, kTileCols), f->sz.n_row_chunks);
   eval_loss_kernel<<<grid, kThreads, 0, s>>>(a);
   BRIE_CUDA(cudaGetLastError());
   const dim3 g2((unsigned)ceil_div(d.ld, 256), d.n_models);

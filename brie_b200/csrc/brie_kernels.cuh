@@ -168,54 +168,94 @@ struct StepTraits {
   static constexpr int NCELL = KG + (CELL ? 2 : 0);
 };
 
+// Events per lane of the step kernel: 4 (one 16-byte access per array) while the per-event
+// accumulators and weights of a lane, 2 x KC x EPL registers, fit next to the rest; the wide
+// covariate case (KC = 16) runs with 2 events per lane (8-byte accesses, 64-event tiles).
+__host__ __device__ constexpr int step_epl(int KC) { return KC > 8 ? 2 : 4; }
+
+template <int EPL> struct LaneVec;
+template <> struct LaneVec<4> { using type = float4; };
+template <> struct LaneVec<2> { using type = float2; };
+template <> struct LaneVec<1> { using type = float; };
+
+template <int EPL>
+__device__ __forceinline__ void vec_get(const typename LaneVec<EPL>::type& v, float (&x)[EPL]);
+template <> __device__ __forceinline__ void vec_get<4>(const float4& v, float (&x)[4]) { x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+template <> __device__ __forceinline__ void vec_get<2>(const float2& v, float (&x)[2]) { x[0] = v.x; x[1] = v.y; }
+template <> __device__ __forceinline__ void vec_get<1>(const float& v, float (&x)[1]) { x[0] = v; }
+
+template <int EPL>
+__device__ __forceinline__ typename LaneVec<EPL>::type vec_make(const float (&x)[EPL]);
+template <> __device__ __forceinline__ float4 vec_make<4>(const float (&x)[4]) { return make_float4(x[0], x[1], x[2], x[3]); }
+template <> __device__ __forceinline__ float2 vec_make<2>(const float (&x)[2]) { return make_float2(x[0], x[1]); }
+template <> __device__ __forceinline__ float vec_make<1>(const float (&x)[1]) { return x[0]; }
+
+// cp.async of one lane's EPL floats; .cg (L2 only) needs 16 bytes, narrower copies use .ca
+template <int BYTES>
+__device__ __forceinline__ void cp_async_lane(uint32_t dst_smem, const void* src, bool valid) {
+  if (BYTES == 16)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(valid ? 16 : 0) : "memory");
+  else if (BYTES == 8)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst_smem), "l"(src), "r"(valid ? 8 : 0) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(valid ? 4 : 0) : "memory");
+}
+
 // Fused ELBO forward + backward + Adam for the per-element variables.
 // grid = (M, n_col_tiles, n_row_chunks): models fastest so the CTAs sharing a
 // count tile are co-resident and the counts are fetched from HBM once.
 //
-// Each warp walks its rows of one 128-event segment through a private two-stage
-// shared-memory ring filled with cp.async (16 B per lane per array, 9 arrays =
-// 4.6 KB per row): the next row streams in from HBM while the current one is
+// Each warp walks its rows of one (32 x EPL)-event segment through a private two-stage
+// shared-memory ring filled with cp.async (EPL floats per lane per array, 9 arrays =
+// 4.6 KB per row at EPL = 4): the next row streams in from HBM while the current one is
 // processed, so loads in flight do not depend on register-resident state.  A lane
 // reads back exactly the bytes it copied, so the ring needs no barrier.
 // One row is processed in three phases:
-//   A (dense, lane = 4 events): KL terms and gradients, shared-parameter
+//   A (dense, lane = EPL events): KL terms and gradients, shared-parameter
 //     accumulators; elements with reads (n > 0) are pushed, compacted by ballot/popc
 //     prefix, into the warp's shared-memory work queue;
 //   B (compacted): lanes take queue items round-robin and run the S Monte-Carlo
 //     samples (Philox + Box-Muller + likelihood gradient) -- zero-count elements,
 //     80-87 % of real data, cost nothing here and the lanes stay converged;
-//   C (dense): owners read their MC sums back, Adam-update and store (16 B stores).
+//   C (dense): owners read their MC sums back, Adam-update and store (16 B stores at EPL = 4).
 constexpr int kQueueFields = 6;   // mu, s, c1, c2, c3, column  ->  results overwrite c1, c2, c3
 constexpr int kRingArrays = 9;    // Z_loc, Z_std_log, c1, c2, c3, m_loc, v_loc, m_std, v_std
 constexpr int kRingStages = 2;
-constexpr int kStepSmemFloats =
-    kWarps * kRingStages * kRingArrays * kTileCols + kWarps * kQueueFields * kTileCols + 6 * kTileCols;
-constexpr int kStepSmemBytes = kStepSmemFloats * 4;
+__host__ __device__ constexpr int step_tile_cols(int KC) { return 32 * step_epl(KC); }
+__host__ __device__ constexpr int step_smem_bytes(int KC) {
+  return (kWarps * kRingStages * kRingArrays + kWarps * kQueueFields + 6) * step_tile_cols(KC) * 4;
+}
 
 template <int KC, int KG, bool CELL, bool LOSS>
 __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(const StepArgs a) {
   using T = StepTraits<KC, KG, CELL, LOSS>;
   constexpr int NEV = T::NEV;
   constexpr int NCELL = T::NCELL;
+  constexpr int EPL = step_epl(KC);
+  constexpr int TC = 32 * EPL;              // events per warp row segment (column tile)
+  using Vec = typename LaneVec<EPL>::type;
   const int m = blockIdx.x;
   if (!((a.model_mask >> m) & 1u)) return;
   const int tile = blockIdx.y;
   const int chunk = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t g0 = (int64_t)tile * kTileCols + lane * 4;
-  const bool in_ld = g0 < a.ld;
+  const int64_t g0 = (int64_t)tile * TC + lane * EPL;
+  const bool in_ld = g0 < a.ld;             // ld % 4 == 0 and EPL divides 4: a lane is all in or all out
 
-  uint32_t act4 = 0;
-  if (in_ld) act4 = *reinterpret_cast<const uint32_t*>(a.active + (int64_t)m * a.ld + g0);
-  if (!__syncthreads_or(act4 != 0)) return;
+  uint32_t act = 0;                         // bit j: this lane's event j is still being optimised
+  if (in_ld) {
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) act |= (a.active[(int64_t)m * a.ld + g0 + j] != 0 ? 1u : 0u) << j;
+  }
+  if (!__syncthreads_or(act != 0)) return;
+  const bool all_act = act == (1u << EPL) - 1u;
 
   extern __shared__ __align__(128) float smem[];
-  float* s_ring = smem + warp * (kRingStages * kRingArrays * kTileCols);
-  float(*q)[kTileCols] =
-      reinterpret_cast<float(*)[kTileCols]>(smem + kWarps * kRingStages * kRingArrays * kTileCols +
-                                            warp * kQueueFields * kTileCols);
-  float(*s_L)[kTileCols] = reinterpret_cast<float(*)[kTileCols]>(
-      smem + kWarps * kRingStages * kRingArrays * kTileCols + kWarps * kQueueFields * kTileCols);
+  float* s_ring = smem + warp * (kRingStages * kRingArrays * TC);
+  float(*q)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * kRingArrays * TC +
+                                                 warp * kQueueFields * TC);
+  float(*s_L)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * kRingArrays * TC +
+                                                   kWarps * kQueueFields * TC);
 
   const int64_t row_begin = (int64_t)chunk * a.rows_per_cta;
   const int64_t row_end = min(row_begin + (int64_t)a.rows_per_cta, a.Nc);
@@ -223,29 +263,29 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   const int64_t mplane = (int64_t)a.M * plane;
   const bool has_c3 = a.c[2] != nullptr;
 
-  // ring producer: this lane's 16-byte column of each array, one commit group per row
-  const uint32_t ring_lane = (uint32_t)__cvta_generic_to_shared(s_ring) + lane * 16;
+  // ring producer: this lane's EPL-float column of each array, one commit group per row
+  const uint32_t ring_lane = (uint32_t)__cvta_generic_to_shared(s_ring) + lane * (EPL * 4);
   auto issue_row = [&](int64_t row, int stage) {
     const bool ok = in_ld && row < row_end;
     const int64_t off = ok ? row * a.ld + g0 : 0;
     const int64_t moff = ok ? (int64_t)m * plane + off : 0;
-    const uint32_t dst = ring_lane + stage * (kRingArrays * kTileCols * 4);
-    cp_async16(dst + 0 * kTileCols * 4, a.Zl + moff, ok);
-    cp_async16(dst + 1 * kTileCols * 4, a.Zs + moff, ok);
-    cp_async16(dst + 2 * kTileCols * 4, a.c[0] + off, ok);
-    cp_async16(dst + 3 * kTileCols * 4, a.c[1] + off, ok);
-    cp_async16(dst + 4 * kTileCols * 4, has_c3 ? a.c[2] + off : a.c[0], ok && has_c3);
-    cp_async16(dst + 5 * kTileCols * 4, a.aZ + moff, ok);
-    cp_async16(dst + 6 * kTileCols * 4, a.aZ + mplane + moff, ok);
-    cp_async16(dst + 7 * kTileCols * 4, a.aZ + 2 * mplane + moff, ok);
-    cp_async16(dst + 8 * kTileCols * 4, a.aZ + 3 * mplane + moff, ok);
+    const uint32_t dst = ring_lane + stage * (kRingArrays * TC * 4);
+    cp_async_lane<EPL * 4>(dst + 0 * TC * 4, a.Zl + moff, ok);
+    cp_async_lane<EPL * 4>(dst + 1 * TC * 4, a.Zs + moff, ok);
+    cp_async_lane<EPL * 4>(dst + 2 * TC * 4, a.c[0] + off, ok);
+    cp_async_lane<EPL * 4>(dst + 3 * TC * 4, a.c[1] + off, ok);
+    cp_async_lane<EPL * 4>(dst + 4 * TC * 4, has_c3 ? a.c[2] + off : a.c[0], ok && has_c3);
+    cp_async_lane<EPL * 4>(dst + 5 * TC * 4, a.aZ + moff, ok);
+    cp_async_lane<EPL * 4>(dst + 6 * TC * 4, a.aZ + mplane + moff, ok);
+    cp_async_lane<EPL * 4>(dst + 7 * TC * 4, a.aZ + 2 * mplane + moff, ok);
+    cp_async_lane<EPL * 4>(dst + 8 * TC * 4, a.aZ + 3 * mplane + moff, ok);
     cp_async_commit();
   };
   issue_row(row_begin + warp, 0);
 
   // per-event constants
-  if (threadIdx.x < kTileCols) {
-    const int64_t g = (int64_t)tile * kTileCols + threadIdx.x;
+  if (threadIdx.x < TC) {
+    const int64_t g = (int64_t)tile * TC + threadIdx.x;
     float l1 = 1.f, l2 = 1.f, l3 = 0.f;
     if (a.eff && g < a.ld) { l1 = a.eff[g]; l2 = a.eff[a.ld + g]; l3 = a.eff[2 * a.ld + g]; }
     s_L[0][threadIdx.x] = l1; s_L[1][threadIdx.x] = l2; s_L[2][threadIdx.x] = l3;
@@ -254,53 +294,48 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       s_L[5][threadIdx.x] = a.eff ? logf(l3) : 0.f;
     }
   }
-  float wc[KC > 0 ? KC : 1][4];
-  float xg[KG > 0 ? KG : 1][4];
-  float bb[4], tau[4], is2[4];
+  float wc[KC > 0 ? KC : 1][EPL];
+  float xg[KG > 0 ? KG : 1][EPL];
+  float bb[EPL], tau[EPL], is2[EPL];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < EPL; ++j) {
     bb[j] = 0.f; tau[j] = 0.f; is2[j] = 1.f;
   }
 #pragma unroll
   for (int k = 0; k < (KC > 0 ? KC : 1); ++k)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) wc[k][j] = 0.f;
+    for (int j = 0; j < EPL; ++j) wc[k][j] = 0.f;
 #pragma unroll
   for (int k = 0; k < (KG > 0 ? KG : 1); ++k)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) xg[k][j] = 0.f;
+    for (int j = 0; j < EPL; ++j) xg[k][j] = 0.f;
   if (in_ld) {
 #pragma unroll
-    for (int k = 0; k < KC; ++k) {
-      const float4 v = *reinterpret_cast<const float4*>(a.Wc + ((int64_t)m * KC + k) * a.ld + g0);
-      wc[k][0] = v.x; wc[k][1] = v.y; wc[k][2] = v.z; wc[k][3] = v.w;
-    }
+    for (int k = 0; k < KC; ++k)
+      vec_get<EPL>(*reinterpret_cast<const Vec*>(a.Wc + ((int64_t)m * KC + k) * a.ld + g0), wc[k]);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < EPL; ++j) {
 #pragma unroll
       for (int k = 0; k < KG; ++k) xg[k][j] = (g0 + j) < a.Ng ? a.Xg[(g0 + j) * KG + k] : 0.f;
     }
     if (!CELL) {
-      const float4 vb = *reinterpret_cast<const float4*>(a.b + (int64_t)m * a.ld + g0);
-      const float4 vt = *reinterpret_cast<const float4*>(a.tau + (int64_t)m * a.ld + g0);
-      bb[0] = vb.x; bb[1] = vb.y; bb[2] = vb.z; bb[3] = vb.w;
-      tau[0] = vt.x; tau[1] = vt.y; tau[2] = vt.z; tau[3] = vt.w;
+      vec_get<EPL>(*reinterpret_cast<const Vec*>(a.b + (int64_t)m * a.ld + g0), bb);
+      vec_get<EPL>(*reinterpret_cast<const Vec*>(a.tau + (int64_t)m * a.ld + g0), tau);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) is2[j] = fast_exp(-2.0f * tau[j]);
+      for (int j = 0; j < EPL; ++j) is2[j] = fast_exp(-2.0f * tau[j]);
     }
   }
   __syncthreads();  // s_L visible
 
-  float acc[NEV > 0 ? NEV : 1][4];
+  float acc[NEV > 0 ? NEV : 1][EPL];
 #pragma unroll
   for (int i = 0; i < (NEV > 0 ? NEV : 1); ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < EPL; ++j) acc[i][j] = 0.f;
 
   const uint32_t stream0 = brie_stream_word(BRIE_PHASE_TRAIN, (uint32_t)a.model_id[m], 0u);
-  const uint32_t ev0 = (uint32_t)(a.event_offset + (int64_t)tile * kTileCols);
+  const uint32_t ev0 = (uint32_t)(a.event_offset + (int64_t)tile * TC);
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const bool all_act = act4 == 0x01010101u;
 
   // per-row (cell) constants are warp-uniform loads; fetch them one row ahead so their latency
   // overlaps the current row's work like the ring does for the big arrays
@@ -329,12 +364,13 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     issue_row(row + kWarps, stage ^ 1);   // prefetch the next row (zero-size copies past the end)
     load_row_consts(row + kWarps);
     cp_async_wait<1>();                   // this row's group has landed
-    const float4* st = reinterpret_cast<const float4*>(s_ring + stage * (kRingArrays * kTileCols)) + lane;
-    const float4 zmu = st[0 * (kTileCols / 4)], zlam = st[1 * (kTileCols / 4)];
-    const float4 zc1 = st[2 * (kTileCols / 4)], zc2 = st[3 * (kTileCols / 4)], zc3 = st[4 * (kTileCols / 4)];
-    float mu[4] = {zmu.x, zmu.y, zmu.z, zmu.w}, lam[4] = {zlam.x, zlam.y, zlam.z, zlam.w};
-    const float c1[4] = {zc1.x, zc1.y, zc1.z, zc1.w}, c2[4] = {zc2.x, zc2.y, zc2.z, zc2.w};
-    const float c3[4] = {zc3.x, zc3.y, zc3.z, zc3.w};
+    const Vec* st = reinterpret_cast<const Vec*>(s_ring + stage * (kRingArrays * TC)) + lane;
+    float mu[EPL], lam[EPL], c1[EPL], c2[EPL], c3[EPL];
+    vec_get<EPL>(st[0 * 32], mu);
+    vec_get<EPL>(st[1 * 32], lam);
+    vec_get<EPL>(st[2 * 32], c1);
+    vec_get<EPL>(st[3 * 32], c2);
+    vec_get<EPL>(st[4 * 32], c3);
     float is2_row = 1.f;
     if (CELL) is2_row = fast_exp(-2.0f * tau_row);
     float cacc[NCELL > 0 ? NCELL : 1];
@@ -342,10 +378,10 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     for (int i = 0; i < (NCELL > 0 ? NCELL : 1); ++i) cacc[i] = 0.f;
 
     // ---- phase A: KL terms, shared-parameter accumulators, non-zero detection ----
-    float gmu[4], glam[4];
+    float gmu[EPL], glam[EPL];
     uint32_t nz = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < EPL; ++j) {
       const float tj = CELL ? tau_row : tau[j];
       const float i2 = CELL ? is2_row : is2[j];
       float pm = CELL ? b_row : bb[j];
@@ -380,25 +416,31 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     }
 
     // ---- phase B: compacted Monte-Carlo work ----
-    const uint32_t b0 = __ballot_sync(0xffffffffu, nz & 1u), b1 = __ballot_sync(0xffffffffu, nz & 2u);
-    const uint32_t b2 = __ballot_sync(0xffffffffu, nz & 4u), b3 = __ballot_sync(0xffffffffu, nz & 8u);
+    uint32_t bal[EPL];
+    int base = 0;
 #ifdef BRIE_SKELETON   // measurement aid (scripts/ab.sh): memory skeleton only, no Monte-Carlo work
     const int n_items = 0;
 #else
-    const int n_items = __popc(b0) + __popc(b1) + __popc(b2) + __popc(b3);
+    int n_items = 0;
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) {
+      bal[j] = __ballot_sync(0xffffffffu, nz & (1u << j));
+      n_items += __popc(bal[j]);
+    }
 #endif
     if (n_items > 0) {
-      const int base = __popc(b0 & lt_mask) + __popc(b1 & lt_mask) + __popc(b2 & lt_mask) + __popc(b3 & lt_mask);
+#pragma unroll
+      for (int j = 0; j < EPL; ++j) base += __popc(bal[j] & lt_mask);
       int pos = base;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < EPL; ++j) {
         if ((nz >> j) & 1u) {
           q[0][pos] = mu[j];
           q[1][pos] = fast_exp(lam[j]);
           q[2][pos] = c1[j];
           q[3][pos] = c2[j];
           q[4][pos] = c3[j];
-          q[5][pos] = __int_as_float(lane * 4 + j);
+          q[5][pos] = __int_as_float(lane * EPL + j);
           ++pos;
         }
       }
@@ -419,7 +461,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       __syncwarp();
       pos = base;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < EPL; ++j) {
         if ((nz >> j) & 1u) {
           gmu[j] -= q[2][pos];
           glam[j] -= q[3][pos];
@@ -431,22 +473,23 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     }
 
     // ---- phase C: Adam on Z_loc / Z_std_log, clip, store ----
-    if (in_ld && act4 != 0) {
-      const float4 zm1 = st[5 * (kTileCols / 4)], zv1 = st[6 * (kTileCols / 4)];
-      const float4 zm2 = st[7 * (kTileCols / 4)], zv2 = st[8 * (kTileCols / 4)];
-      float m1[4] = {zm1.x, zm1.y, zm1.z, zm1.w}, v1[4] = {zv1.x, zv1.y, zv1.z, zv1.w};
-      float m2[4] = {zm2.x, zm2.y, zm2.z, zm2.w}, v2[4] = {zv2.x, zv2.y, zv2.z, zv2.w};
+    if (act != 0) {
+      float m1[EPL], v1[EPL], m2[EPL], v2[EPL];
+      vec_get<EPL>(st[5 * 32], m1);
+      vec_get<EPL>(st[6 * 32], v1);
+      vec_get<EPL>(st[7 * 32], m2);
+      vec_get<EPL>(st[8 * 32], v2);
       if (all_act) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < EPL; ++j) {
           adam_update(mu[j], m1[j], v1[j], gmu[j], a.alpha);
           adam_update(lam[j], m2[j], v2[j], glam[j], a.alpha);
           mu[j] = clip9(mu[j]);  // Variable constraint (model_TFProb.py:80-81)
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if ((act4 >> (8 * j)) & 0xffu) {
+        for (int j = 0; j < EPL; ++j) {
+          if ((act >> j) & 1u) {
             adam_update(mu[j], m1[j], v1[j], gmu[j], a.alpha);
             adam_update(lam[j], m2[j], v2[j], glam[j], a.alpha);
             mu[j] = clip9(mu[j]);
@@ -454,12 +497,12 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
         }
       }
       const int64_t moff = (int64_t)m * plane + row * a.ld + g0;
-      __stcs(reinterpret_cast<float4*>(a.Zl + moff), make_float4(mu[0], mu[1], mu[2], mu[3]));
-      __stcs(reinterpret_cast<float4*>(a.Zs + moff), make_float4(lam[0], lam[1], lam[2], lam[3]));
-      __stcs(reinterpret_cast<float4*>(a.aZ + moff), make_float4(m1[0], m1[1], m1[2], m1[3]));
-      __stcs(reinterpret_cast<float4*>(a.aZ + mplane + moff), make_float4(v1[0], v1[1], v1[2], v1[3]));
-      __stcs(reinterpret_cast<float4*>(a.aZ + 2 * mplane + moff), make_float4(m2[0], m2[1], m2[2], m2[3]));
-      __stcs(reinterpret_cast<float4*>(a.aZ + 3 * mplane + moff), make_float4(v2[0], v2[1], v2[2], v2[3]));
+      __stcs(reinterpret_cast<Vec*>(a.Zl + moff), vec_make<EPL>(mu));
+      __stcs(reinterpret_cast<Vec*>(a.Zs + moff), vec_make<EPL>(lam));
+      __stcs(reinterpret_cast<Vec*>(a.aZ + moff), vec_make<EPL>(m1));
+      __stcs(reinterpret_cast<Vec*>(a.aZ + mplane + moff), vec_make<EPL>(v1));
+      __stcs(reinterpret_cast<Vec*>(a.aZ + 2 * mplane + moff), vec_make<EPL>(m2));
+      __stcs(reinterpret_cast<Vec*>(a.aZ + 3 * mplane + moff), vec_make<EPL>(v2));
     }
     if (NCELL > 0) {
 #pragma unroll
@@ -473,13 +516,13 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 
   if (NEV > 0) {
     __syncthreads();  // all warps are done with their queues; reuse the memory for the reduction
-    float(*red)[kTileCols] = reinterpret_cast<float(*)[kTileCols]>(smem + kWarps * kRingStages * kRingArrays * kTileCols);
-    const int64_t gcol = (int64_t)tile * kTileCols + threadIdx.x;
+    float(*red)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * kRingArrays * TC);
+    const int64_t gcol = (int64_t)tile * TC + threadIdx.x;
 #pragma unroll
     for (int i = 0; i < NEV; ++i) {
-      *reinterpret_cast<float4*>(&red[warp][lane * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      *reinterpret_cast<Vec*>(&red[warp][lane * EPL]) = vec_make<EPL>(acc[i]);
       __syncthreads();
-      if (threadIdx.x < kTileCols && gcol < a.ld) {
+      if (threadIdx.x < TC && gcol < a.ld) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
@@ -507,7 +550,7 @@ struct EventArgs {
   uint32_t xc_mask[kMaxModels];
 };
 
-constexpr int kMaxNEV = 11;  // BRIE_MAX_KC + 2 + 1
+constexpr int kMaxNEV = 19;  // BRIE_MAX_KC + 2 + 1
 
 // block = 8 warps x 32 events: warp w sums row chunks w, w+8, ... (coalesced 128-byte rows of the
 // partial buffer), warp 0 combines the 8 sub-sums in fixed order (f64) and applies the updates.

@@ -17,7 +17,7 @@ import torch
 from . import _lib
 
 LEARNING_RATES = [0.001, 0.005, 0.01, 0.02, 0.01, 0.005]   # model_TFProb.py:234
-KC_SUPPORTED = (0, 1, 2, 4, 8)
+KC_SUPPORTED = (0, 1, 2, 4, 8, 16)
 KG_SUPPORTED = (0, 4, 8)
 
 

@@ -22,6 +22,11 @@ def make_design(Nc, kind, rng):
                                rng.standard_normal((Nc, 1))], axis=1).astype(np.float32)
     if kind == 'pseudotime':                      # C5
         return rng.uniform(0, 1, (Nc, 1)).astype(np.float32)
+    if kind == 'wide15':                          # dentate-gyrus design: detection rate + 14 cluster indicators
+        X = np.zeros((Nc, 15), np.float32)            # (brie-tutorials/dentateGyrus/data/dentategyrus_cdr_cluster.tsv)
+        X[:, 0] = rng.uniform(0.02, 0.3, Nc)
+        X[np.arange(Nc), 1 + rng.integers(0, 14, Nc)] = 1
+        return X
     raise ValueError(kind)
 
 

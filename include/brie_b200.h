@@ -36,7 +36,7 @@ extern "C" {
 
 #define BRIE_ABI_VERSION 1
 #define BRIE_MAX_MODELS 32
-#define BRIE_MAX_KC 8
+#define BRIE_MAX_KC 16
 #define BRIE_MAX_KG 8
 
 #define BRIE_OK 0

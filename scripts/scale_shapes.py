@@ -3,6 +3,8 @@
   C3 slab : 100k cells x 2048 events, Kc=3 (+LRT on all 3 -> M=4), 3 layers + effLen, gene intercept
   C4 slab : 200k cells x 4096 genes, spliced/unspliced (2 layers, no effLen), Kg=8, interceptMode cell, M=1
   C5 slab : 1M cells x 512 events, pseudotime covariate + LRT (M=2)
+  W16     : 20k cells x 4096 genes, 15 covariates (detection rate + 14 cluster indicators, the dentate-gyrus
+            design) in one model -> the 2-events-per-lane instantiation (Kc 15 -> 16)
 Prints one JSON line per shape: ms/step, cell*event*sample/s, algorithmic GB/s and fraction of measured HBM.
 """
 import json, os, sys, time
@@ -19,6 +21,7 @@ SHAPES = {
     "C3": dict(Nc=100000, Ng=2048, design='mixed3', eff=True, layers=3,
                masks=[[0, 1, 2], [1, 2], [0, 2], [0, 1]], mode='gene', Kg=0),
     "C4": dict(Nc=200000, Ng=4096, design='none', eff=False, layers=2, masks=[[]], mode='cell', Kg=8),
+    "W16": dict(Nc=20000, Ng=4096, design='wide15', eff=False, layers=2, masks=[list(range(15))], mode='gene', Kg=0),
     "C5": dict(Nc=1000000, Ng=512, design='pseudotime', eff=True, layers=3, masks=[[0], []], mode='gene', Kg=0),
 }
 

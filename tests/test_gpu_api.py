@@ -256,5 +256,9 @@ def test_one_vs_rest_lrt_with_15_covariates_null_base():
     assert np.abs(res.ELBO_gain - ref.ELBO_gain).max() < 2e-2
     eng = FitEngine([x.copy() for x in data], Xc=Xc, masks=[[0]] + [[0, k] for k in range(1, T + 1)])
     assert eng.Kc == 2 and eng.Xc.shape == (1 + T, Nc, 2)
+    # the same design in full mode (each refit drops one of the 15 columns) needs width 15 -> 16
+    eng = FitEngine([x.copy() for x in data], Xc=Xc, masks=[list(range(15))] + [[k for k in range(15) if k != i]
+                                                                               for i in range(1, 15)])
+    assert eng.Kc == 16 and eng.sizes.n_col_tiles == 1
     with pytest.raises(ValueError, match="exceeds the supported maximum"):
         FitEngine([x.copy() for x in data], Xc=np.ones((Nc, 40), np.float32))

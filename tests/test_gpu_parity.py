@@ -50,6 +50,9 @@ CASES = [
     ('gene', True, 3, 1, 3, None, None),     # gene features
     ('cell', False, 2, 1, 2, None, None),    # DMG-style: per-cell intercept + gene features
     ('cell', True, 3, 0, 0, None, 2.0),      # fixed sigma
+    ('gene', True, 3, 11, 0, None, None),    # wide covariates: Kc 11 -> 16, two events per lane, 64-event tiles
+    ('cell', False, 2, 9, 5, None, None),    # wide covariates + gene features + per-cell intercept
+    ('gene', True, 3, 7, 0, None, None),     # Kc 7 -> 8
 ]
 
 
@@ -109,7 +112,7 @@ def test_first_step_loss_and_gradients(mode, eff, n_layers, Kc, Kg, intercept, s
         close(10 * cellp[:, :Kg], grads['Wg_loc'], 'Wg')
 
 
-@pytest.mark.parametrize("mode,eff,n_layers,Kc,Kg,intercept,sigma", [CASES[1], CASES[4], CASES[6]])
+@pytest.mark.parametrize("mode,eff,n_layers,Kc,Kg,intercept,sigma", [CASES[1], CASES[4], CASES[6], CASES[8]])
 def test_trajectory_parity(mode, eff, n_layers, Kc, Kg, intercept, sigma):
     """60 optimisation steps (2 Adam stages) track the float32 oracle step for step."""
     Nc, Ng, S, seed = 96, 131, 3, 5
