@@ -8,6 +8,8 @@ import ctypes as C
 import os
 
 BRIE_MAX_MODELS = 32
+ABI_VERSION = 2
+TARGETS = {"ELBO": 0, "marginLik": 1}
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BRIE_LIB_PATH", os.path.join(_HERE, "libbrie_b200.so"))
 
@@ -20,6 +22,7 @@ class FitDesc(C.Structure):
         ("mc_size", C.c_int32), ("n_layers", C.c_int32), ("has_efflen", C.c_int32),
         ("cell_mode", C.c_int32), ("train_intercept", C.c_int32),
         ("train_sigma", C.c_int32), ("trace_cap", C.c_int32),
+        ("target", C.c_int32), ("reserved0", C.c_int32),
         ("model_id", C.c_int32 * BRIE_MAX_MODELS),
         ("xc_mask", C.c_uint32 * BRIE_MAX_MODELS),
     ]
@@ -94,7 +97,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.brie_abi_version() != 1:
+    if lib.brie_abi_version() != ABI_VERSION:
         raise RuntimeError("brie_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -13,6 +13,7 @@
 
 #include "../../include/brie_b200.h"
 #include "brie_kernels.cuh"
+#include "brie_margin.cuh"
 
 #include "brie_host.h"
 
@@ -132,6 +133,8 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
   if (d.mc_size < 1 || d.mc_size > 4096) return fail(BRIE_ERR_ARG, "mc_size out of range");
   if (d.n_layers != 2 && d.n_layers != 3) return fail(BRIE_ERR_ARG, "n_layers must be 2 or 3");
   if (d.trace_cap < 0) return fail(BRIE_ERR_ARG, "trace_cap must be >= 0");
+  if (d.target != BRIE_TARGET_ELBO && d.target != BRIE_TARGET_MARGINLIK)
+    return fail(BRIE_ERR_ARG, "target must be BRIE_TARGET_ELBO or BRIE_TARGET_MARGINLIK");
   for (int m = 0; m < d.n_models; ++m) {
     if (d.model_id[m] < 0 || d.model_id[m] >= 4096) return fail(BRIE_ERR_ARG, "model_id must be in [0, 4096)");
     if ((d.xc_mask[m] >> d.Kc) != 0) return fail(BRIE_ERR_ARG, "xc_mask has bits beyond Kc");
@@ -327,6 +330,38 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
     f->t += 1;
     const double t = (double)f->t;
     f->alpha = (float)((double)f->lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
+    const bool margin = d.target == BRIE_TARGET_MARGINLIK;
+    int nev = d.Kc + (d.cell_mode ? 0 : 2) + (loss ? 1 : 0);
+    int cell_tiles = f->sz.n_col_tiles;
+    if (margin) {
+      // prior-sampled objective: counts only, no per-element state (brie_margin.cuh)
+      nev = d.Kc + (d.cell_mode ? 0 : 2) + 1;
+      cell_tiles = (int)ceil_div(d.ld, kMarginTile);
+      MarginArgs g;
+      memset(&g, 0, sizeof g);
+      g.Nc = d.n_cells; g.Ng = d.n_events; g.ld = d.ld; g.event_offset = d.event_offset; g.seed = d.seed;
+      g.c[0] = f->buf.counts[0]; g.c[1] = f->buf.counts[1]; g.c[2] = f->buf.counts[2];
+      g.eff = f->buf.efflen3; g.Xc = f->buf.Xc; g.Xg = f->buf.Xg;
+      g.Wc = f->buf.Wc; g.b = f->buf.intercept; g.tau = f->buf.sigma_log; g.Wg = f->buf.Wg;
+      g.active = f->buf.active;
+      g.part_ev = scratch + f->off_part_ev;
+      g.part_cell = scratch + f->off_part_cell;
+      g.step = f->global_step; g.model_mask = mmask;
+      g.M = M; g.S = d.mc_size; g.rows_per_cta = f->sz.rows_per_cta;
+      g.KC = d.Kc; g.KG = d.Kg; g.cell_mode = d.cell_mode; g.NEV = nev; g.NCELL = f->ncell;
+      for (int m = 0; m < M; ++m) g.model_id[m] = d.model_id[m];
+      const size_t smem = (size_t)kWarps * nev * kMarginTile * sizeof(float);
+      static bool configured = false;
+      if (!configured) {
+        BRIE_CUDA(cudaFuncSetAttribute(margin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       kWarps * (BRIE_MAX_KC + 3) * kMarginTile * (int)sizeof(float)));
+        configured = true;
+      }
+      const dim3 grid(M, cell_tiles, f->sz.n_row_chunks);
+      margin_step_kernel<<<grid, kThreads, smem, s>>>(g);
+      BRIE_CUDA(cudaGetLastError());
+      f->launches += 1;
+    } else {
     StepArgs a;
     memset(&a, 0, sizeof a);
     a.Nc = d.n_cells; a.Ng = d.n_events; a.ld = d.ld; a.event_offset = d.event_offset; a.seed = d.seed;
@@ -349,15 +384,15 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
     BRIE_CUDA(dispatch_step(a, d.Kc, d.Kg, d.cell_mode != 0, loss, grid, s));
     if (timed) BRIE_CUDA(cudaEventRecord(f->ev1[f->ev_used++], s));
     f->launches += 1;
+    }
 
-    const int nev = d.Kc + (d.cell_mode ? 0 : 2) + (loss ? 1 : 0);
     if (nev > 0) {
       EventArgs e;
       memset(&e, 0, sizeof e);
       e.ld = d.ld; e.Ng = d.n_events; e.M = M; e.KC = d.Kc; e.NEV = nev; e.n_chunks = f->sz.n_row_chunks;
       e.idx_gb = d.cell_mode ? -1 : d.Kc;
       e.idx_gt = d.cell_mode ? -1 : d.Kc + 1;
-      e.idx_loss = loss ? d.Kc + (d.cell_mode ? 0 : 2) : -1;
+      e.idx_loss = (loss || margin) ? d.Kc + (d.cell_mode ? 0 : 2) : -1;   // trace written only if trace_slot >= 0
       e.train_b = d.train_intercept; e.train_tau = d.train_sigma;
       e.trace_slot = trace_slot; e.trace_cap = d.trace_cap;
       e.alpha = f->alpha;
@@ -375,7 +410,7 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
     if (f->ncell > 0) {
       CellArgs c;
       memset(&c, 0, sizeof c);
-      c.Nc = d.n_cells; c.M = M; c.KG = d.Kg; c.NCELL = f->ncell; c.n_tiles = f->sz.n_col_tiles;
+      c.Nc = d.n_cells; c.M = M; c.KG = d.Kg; c.NCELL = f->ncell; c.n_tiles = cell_tiles;
       c.model_mask = mmask;
       c.part_cell = scratch + f->off_part_cell;
       c.G = scratch + f->off_G;
@@ -448,6 +483,7 @@ int brie_fit_eval_loss_gene(brie_fit* f, int32_t n_eval, int32_t mc_size, float*
   a.part_ev = scratch + f->off_part_ev;
   a.M = d.n_models; a.S = mc_size; a.n_eval = n_eval; a.rows_per_cta = f->sz.rows_per_cta;
   a.KC = d.Kc; a.KG = d.Kg; a.cell_mode = d.cell_mode;
+  a.margin = d.target == BRIE_TARGET_MARGINLIK;
   for (int m = 0; m < d.n_models; ++m) a.model_id[m] = d.model_id[m];
   const dim3 grid(d.n_models, (unsigned)ceil_div(d.ld, kTileCols), f->sz.n_row_chunks);
   eval_loss_kernel<<<grid, kThreads, 0, s>>>(a);

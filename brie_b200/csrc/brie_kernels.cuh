@@ -670,18 +670,22 @@ struct EvalArgs {
   const float* Wc; const float* b; const float* tau; const float* Wg;
   float* part_ev;      // (n_row_chunks, M, 2, ld)
   int32_t M, S, n_eval, rows_per_cta, KC, KG, cell_mode;
+  int32_t margin;      // 1: target = "marginLik" -- samples from the prior, log-mean-exp per evaluation, no KL
   int32_t model_id[kMaxModels];
 };
 
 // One element with reads: its n_eval evaluations are spread over the 32 lanes (lane takes
 // evaluations lane, lane+32, ...), so lane utilisation does not depend on the sparsity pattern;
 // the warp sum is a fixed xor-shuffle tree (deterministic).  Returns sum over all samples of
-// c1 log psi + c2 log(1-psi) - n log D  (without the constant sum_k c_k log L_k).
+// c1 log psi + c2 log(1-psi) - n log D  (without the constant sum_k c_k log L_k); with `margin`
+// every evaluation contributes S x log-mean-exp of its S sample log-likelihoods instead
+// (tfp.math.reduce_logmeanexp, model_TFProb.py:188-189), so the caller's 1/(n_eval S) applies to both.
 __device__ __forceinline__ float eval_item(float mu, float s, float c1, float c2, float n, float L1, float L2,
-                                           float L3, bool eff, int n_eval, int S, uint32_t event, uint32_t cell,
-                                           uint32_t stream0, uint64_t seed, int lane) {
+                                           float L3, bool eff, bool margin, int n_eval, int S, uint32_t event,
+                                           uint32_t cell, uint32_t stream0, uint64_t seed, int lane) {
   float acc = 0.f;
   for (int it = lane; it < n_eval; it += 32) {
+    float mx = -INFINITY, Z = 0.f;
     for (int s0 = 0; s0 < S; s0 += 4) {
       float eps[4];
       brie_normals4(event, cell, (uint32_t)it, stream0 + (uint32_t)(s0 >> 2), seed, eps);
@@ -695,10 +699,17 @@ __device__ __forceinline__ float eval_item(float mu, float s, float c1, float c2
           const float psi = z >= 0.f ? inv : e * inv;
           const float qq = z >= 0.f ? e * inv : inv;
           const float D = fmaf(psi, L1, fmaf(qq, L2, L3));
-          acc += fmaf(c1, lsp, c2 * (lsp - z)) - (eff ? n * logf(D) : 0.f);
+          const float l = fmaf(c1, lsp, c2 * (lsp - z)) - (eff ? n * logf(D) : 0.f);
+          if (!margin) {
+            acc += l;
+          } else {
+            if (l > mx) { Z *= expf(mx - l); mx = l; }
+            Z += expf(l - mx);
+          }
         }
       }
     }
+    if (margin) acc += (float)S * (mx + logf(Z) - logf((float)S));
   }
   return warp_sum(acc);
 }
@@ -750,6 +761,7 @@ __global__ void __launch_bounds__(kThreads) eval_loss_kernel(const EvalArgs a) {
       const int64_t gj = g0 + j;
       const bool valid = gj < a.Ng;
       float n = 0.f;
+      float zc = mu[j], zsl = lam[j];       // centre and log-scale the samples are drawn around
       if (valid) {
         const float tj = a.cell_mode ? tau_row : tau[j];
         float pm = a.cell_mode ? b_row : bb[j];
@@ -757,9 +769,13 @@ __global__ void __launch_bounds__(kThreads) eval_loss_kernel(const EvalArgs a) {
           pm = fmaf(a.Xc[((int64_t)m * a.Nc + row) * a.KC + k], a.Wc[((int64_t)m * a.KC + k) * a.ld + gj], pm);
         for (int k = 0; k < a.KG; ++k)
           pm = fmaf(a.Wg[((int64_t)m * a.Nc + row) * a.KG + k], a.Xg[gj * a.KG + k], pm);
-        const float d = lam[j] - tj;
-        const float r0 = (mu[j] - pm) * expf(-tj);
-        kl[j] += 0.5f * r0 * r0 + 0.5f * expm1f(2.0f * d) - d;
+        if (a.margin) {                       // prior samples, no KL term (model_TFProb.py:156-157, 202-205)
+          zc = pm; zsl = tj;
+        } else {
+          const float d = lam[j] - tj;
+          const float r0 = (mu[j] - pm) * expf(-tj);
+          kl[j] += 0.5f * r0 * r0 + 0.5f * expm1f(2.0f * d) - d;
+        }
         n = c1[j] + c2[j] + c3[j];
       }
       // elements with reads, one at a time, all 32 lanes cooperating
@@ -767,14 +783,14 @@ __global__ void __launch_bounds__(kThreads) eval_loss_kernel(const EvalArgs a) {
       while (todo) {
         const int src = __ffs(todo) - 1;
         todo &= todo - 1;
-        const float imu = __shfl_sync(0xffffffffu, mu[j], src), ilam = __shfl_sync(0xffffffffu, lam[j], src);
+        const float imu = __shfl_sync(0xffffffffu, zc, src), ilam = __shfl_sync(0xffffffffu, zsl, src);
         const float ic1 = __shfl_sync(0xffffffffu, c1[j], src), ic2 = __shfl_sync(0xffffffffu, c2[j], src);
         const float in = __shfl_sync(0xffffffffu, n, src);
         const float l1 = __shfl_sync(0xffffffffu, L1[j], src), l2 = __shfl_sync(0xffffffffu, L2[j], src);
         const float l3 = __shfl_sync(0xffffffffu, L3[j], src);
         const uint32_t ev = (uint32_t)(a.event_offset + (int64_t)tile * kTileCols + src * 4 + j);
-        const float tot = eval_item(imu, expf(ilam), ic1, ic2, in, l1, l2, l3, eff, a.n_eval, a.S, ev, (uint32_t)row,
-                                    stream0, a.seed, lane);
+        const float tot = eval_item(imu, expf(ilam), ic1, ic2, in, l1, l2, l3, eff, a.margin != 0, a.n_eval, a.S, ev,
+                                    (uint32_t)row, stream0, a.seed, lane);
         if (lane == src) {
           const float k0 = eff ? fmaf(c1[j], logf(L1[j]), fmaf(c2[j], logf(L2[j]), c3[j] * logf(L3[j]))) : 0.f;
           ll[j] += fmaf(tot, inv_n, k0);

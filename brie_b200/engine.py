@@ -51,6 +51,7 @@ class FitEngine:
     group_size : events per reference batch, ceil(batch_size / Nc) (model_wrap.py:242);
         None = one group (un-batched branch, model_wrap.py:261-269).
     event_offset : global index of this shard's first event.
+    target : "ELBO" (default) or "marginLik" (model_TFProb.py:156-157, 188-189, 202-205).
     dist_group : torch.distributed process group for event-sharded fits with shared
         per-cell parameters (Kg > 0 or intercept_mode 'cell'); None = single GPU.
     """
@@ -58,7 +59,7 @@ class FitEngine:
     def __init__(self, counts, effLen=None, Xc=None, Xg=None, masks=None, model_ids=None,
                  intercept=None, intercept_mode='gene', sigma=None, MC_size=1, seed=0,
                  group_size=None, event_offset=0, n_events_total=None, device=None,
-                 trace_cap=None, dist_group=None, n_events=None):
+                 trace_cap=None, dist_group=None, n_events=None, target="ELBO"):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("brie_b200: no CUDA device (there is no CPU fallback)")
@@ -78,6 +79,9 @@ class FitEngine:
         self.S = int(MC_size)
         self.seed = int(seed)
         self.dist_group = dist_group
+        if target not in _lib.TARGETS:
+            raise ValueError("brie_b200: target must be 'ELBO' or 'marginLik', got %r" % (target,))
+        self.target = target
         Xc = np.zeros((Nc, 0), np.float32) if Xc is None else np.asarray(Xc, np.float32)
         Xg = np.zeros((Ng, 0), np.float32) if Xg is None else np.asarray(Xg, np.float32)
         self.Kc_real, self.Kg_real = Xc.shape[1], Xg.shape[1]
@@ -146,6 +150,7 @@ class FitEngine:
         d.n_layers, d.has_efflen, d.cell_mode = self.n_layers, int(effLen is not None), int(self.cell_mode)
         d.train_intercept, d.train_sigma = int(intercept is None), int(sigma is None)
         d.trace_cap = self.trace_cap
+        d.target = _lib.TARGETS[target]
         for m in range(M):
             d.model_id[m] = self.model_ids[m]
             d.xc_mask[m] = (1 << len(self.masks[m])) - 1

@@ -112,9 +112,9 @@ class BRIE2():
             min_iter=1000, max_iter=5000, add_iter=500, epsilon_conv=1e-2, verbose=True,
             MC_size=1, n_eval=500, **kwargs):
         """Fit the model's parameters (model_TFProb.py:214-273).  `optimizer` and
-        `learn_rate` are ignored exactly as the reference ignores them (:228-237)."""
-        if target != "ELBO":
-            raise NotImplementedError("brie_b200: only target='ELBO' is implemented")
+        `learn_rate` are ignored exactly as the reference ignores them (:228-237).
+        target: "ELBO" or "marginLik" (:156-157, 188-189, 202-205)."""
+        self.target = target
         start_time = time.time()
         from scipy.sparse import issparse
         layers = [(x.toarray() if issparse(x) else np.asarray(x)).astype(np.float32) for x in count_layers]
@@ -126,7 +126,7 @@ class BRIE2():
                                  model_ids=[self._model_id], intercept=self._intercept_const,
                                  intercept_mode=self.intercept_mode, sigma=self._sigma_const,
                                  MC_size=MC_size, seed=self._seed, device=self._device,
-                                 trace_cap=trace_cap)
+                                 trace_cap=trace_cap, target=target)
         self._post_cache = None
         e = self._engine
         e.fit(min_iter=min_iter, max_iter=max_iter, add_iter=add_iter, epsilon_conv=epsilon_conv,

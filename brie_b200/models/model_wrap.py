@@ -135,7 +135,8 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     dist_group = keyargs.pop('dist_group', None)
     n_eval = keyargs.pop('n_eval', 500)
     MC_size = keyargs.pop('MC_size', 1)
-    for k in ('target', 'optimizer', 'learn_rate', 'verbose'):      # accepted and ignored (:214-237)
+    target = keyargs.pop('target', "ELBO")                          # reaches BRIE2.fit through **keyargs (:144)
+    for k in ('optimizer', 'learn_rate', 'verbose'):                # accepted and ignored (:214-237)
         keyargs.pop(k, None)
 
     import torch
@@ -200,7 +201,7 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     common = dict(effLen=effLen, Xc=Xc, Xg=Xg, intercept=intercept, sigma=sigma, MC_size=MC_size,
                   seed=seed, group_size=group_size, event_offset=event_offset,
                   n_events_total=n_events_total, device=dev, trace_cap=trace_cap,
-                  dist_group=dist_group, n_events=Ng)
+                  dist_group=dist_group, n_events=Ng, target=target)
     data = tiles
     cell_mode = intercept_mode.upper() == 'CELL'
     T = len(test_masks)

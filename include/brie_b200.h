@@ -34,10 +34,13 @@
 extern "C" {
 #endif
 
-#define BRIE_ABI_VERSION 1
+#define BRIE_ABI_VERSION 2
 #define BRIE_MAX_MODELS 32
 #define BRIE_MAX_KC 16
 #define BRIE_MAX_KG 8
+
+#define BRIE_TARGET_ELBO 0
+#define BRIE_TARGET_MARGINLIK 1
 
 #define BRIE_OK 0
 #define BRIE_ERR_ARG (-1)
@@ -60,6 +63,8 @@ typedef struct brie_fit_desc {
   int32_t train_intercept;/* intercept is a Variable (model_TFProb.py:67-71) */
   int32_t train_sigma;    /* sigma_log is a Variable (model_TFProb.py:73-78) */
   int32_t trace_cap;      /* slots in loss_trace per model */
+  int32_t target;         /* BRIE_TARGET_ELBO (model_TFProb.py:206-211) or BRIE_TARGET_MARGINLIK (:202-205) */
+  int32_t reserved0;
   int32_t model_id[BRIE_MAX_MODELS]; /* RNG model word of each batched model */
   uint32_t xc_mask[BRIE_MAX_MODELS]; /* bit k set: column k of Xc[model] is a real covariate */
 } brie_fit_desc;

@@ -45,8 +45,9 @@ class EagerBRIE2:
         self.Xc = None
         self.Xg = None
 
-    def variables(self):
-        out = {'Z_loc': self.Z_loc, 'Z_std_log': self.Z_std_log}
+    def variables(self, target="ELBO"):
+        # marginLik never reads the variational parameters (:156-157), so they are not watched
+        out = {'Z_loc': self.Z_loc, 'Z_std_log': self.Z_std_log} if target == "ELBO" else {}
         if self.intercept.requires_grad:
             out['intercept'] = self.intercept
         if self.sigma_log.requires_grad:
@@ -65,9 +66,12 @@ class EagerBRIE2:
             zz = zz + torch.matmul(self.Wg_loc, self.Xg.T)
         return zz + self.intercept
 
-    def logLik_MC(self, count_layers, eps):                      # :130-191
-        Z_std = torch.exp(self.Z_std_log)
-        _Z = self.Z_loc.unsqueeze(0) + Z_std.unsqueeze(0) * eps  # Normal.sample, reparameterised
+    def logLik_MC(self, count_layers, eps, target="ELBO"):       # :130-191
+        if target == "marginLik":                                # Z_prior.sample (:156-157)
+            _Z = self.z_prior_loc().unsqueeze(0) + torch.exp(self.sigma_log).unsqueeze(0) * eps
+        else:
+            Z_std = torch.exp(self.Z_std_log)
+            _Z = self.Z_loc.unsqueeze(0) + Z_std.unsqueeze(0) * eps  # Normal.sample, reparameterised
         ls = torch.nn.functional.logsigmoid
         if self.effLen is None:
             ll = count_layers[0].unsqueeze(0) * ls(_Z) + count_layers[1].unsqueeze(0) * ls(0 - _Z)
@@ -80,6 +84,8 @@ class EagerBRIE2:
                   count_layers[1].unsqueeze(0) * phi_log[:, :, :, 1])
             if len(count_layers) > 2:
                 ll = ll + count_layers[2].unsqueeze(0) * phi_log[:, :, :, 2]
+        if target == "marginLik":                                # tfp.math.reduce_logmeanexp (:188-189)
+            return torch.logsumexp(ll, dim=0) - math.log(ll.shape[0])
         return ll.mean(0)
 
     def kl(self):                                                # tfd.kl_divergence(Normal, Normal)
@@ -89,7 +95,10 @@ class EagerBRIE2:
         return (0.5 * (a_loc / b_scale - b_loc / b_scale) ** 2 +
                 0.5 * torch.expm1(2. * diff_log_scale) - diff_log_scale)
 
-    def get_loss(self, count_layers, eps, axis=None):            # :194-211
+    def get_loss(self, count_layers, eps, axis=None, target="ELBO"):   # :194-211
+        if target == "marginLik":                                # :202-205
+            ll = self.logLik_MC(count_layers, eps, target)
+            return -ll.sum() if axis is None else -ll.sum(axis)
         kl, ll = self.kl(), self.logLik_MC(count_layers, eps)
         if axis is None:
             return kl.sum() - ll.sum()

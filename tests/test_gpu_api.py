@@ -96,8 +96,8 @@ def test_BRIE2_class_protocol_and_null_base_mode():
         assert getattr(m, name).numpy().shape == shape, name
     assert m.Psi95CI.shape == (Nc, Ng) and (m.Psi95CI >= 0).all()
     assert np.abs(m.Z_loc.numpy()).max() <= 9.0
-    with pytest.raises(NotImplementedError):
-        m.fit(d2, Xc=Xc, target="marginLik")
+    with pytest.raises(ValueError, match="target"):
+        m.fit(d2, Xc=Xc, target="nonsense")
 
     res = fit_BRIE_matrix([x.copy() for x in data], Xc=Xc, effLen=effLen, LRT_index=[1], base_mode='null',
                           intercept_mode='gene', min_iter=120, max_iter=120, MC_size=2, n_eval=10, seed=1)

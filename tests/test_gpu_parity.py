@@ -231,3 +231,73 @@ def test_full_fit_with_lrt_matches_oracle(kind):
     print("DAS calls at FDR<0.05: %d of %d" % ((ref.fdr < 0.05).sum(), ref.fdr.size))
     if kind == "planted_dense":
         assert (ref.fdr < 0.05).sum() >= 3
+
+
+MARGIN_CASES = [CASES[1], CASES[3], CASES[4], CASES[5], CASES[6], CASES[8]]
+
+
+@pytest.mark.parametrize("mode,eff,n_layers,Kc,Kg,intercept,sigma", MARGIN_CASES)
+def test_marginlik_step_loss_and_gradients(mode, eff, n_layers, Kc, Kg, intercept, sigma):
+    """target='marginLik' (model_TFProb.py:156-157, 188-189, 202-205): one step's per-event loss and
+    the gradient of every prior parameter equal the oracle's; Z_loc / Z_std_log are not touched."""
+    Nc, Ng, S, seed = 150, 203, 4, 11
+    data, effLen, Xc, Xg = make_problem(Nc, Ng, Kc, Kg, eff, n_layers)
+    add_pseudo_count(data, np.float32(0.01))
+    eng = _engine(data, effLen, Xc, Xg, intercept=intercept, intercept_mode=mode, sigma=sigma, MC_size=S,
+                  seed=seed, trace_cap=8, target="marginLik")
+    eng.init_params()
+    z0 = eng.Z_loc.clone()
+    om = OracleBRIE2(Nc, Ng, Kc, Kg, effLen, intercept, mode, sigma, dtype=np.float64, seed=seed)
+    pr = eng.model_params(0)
+    om.p['Wc_loc'] = pr['Wc_loc'].astype(np.float64)
+    om.p['Wg_loc'] = pr['Wg_loc'].astype(np.float64)
+    om.p['intercept'] = pr['intercept'].astype(np.float64)
+    om.Xc, om.Xg = Xc.astype(np.float64), Xg.astype(np.float64)
+    eps = device_eps_provider(seed, 0, Nc, Ng)(px.PHASE_TRAIN, 0, S)
+    loss, loss_gene, grads = om.loss_and_grads(data, eps, target="marginLik")
+    eng.begin_stage(0.001)
+    eng.run_steps(1, 0)
+    torch.cuda.synchronize()
+    tr = eng.loss_trace[0, 0, :Ng].cpu().numpy()
+    assert np.abs(tr - loss_gene).max() <= 2e-5 * np.abs(loss_gene).max()
+    assert torch.equal(eng.Z_loc, z0) and float(eng.adam_Z.abs().max()) == 0.0
+
+    def close(dev, ref, name):
+        assert np.abs(dev - ref).max() <= 2e-4 * max(np.abs(ref).max(), 1.0), name
+
+    ld, KC, KGp = eng.ld, eng.Kc, eng.Kg
+    small = eng.adam_small.cpu().numpy()
+    ev = small[:2 * (KC + 2) * ld].reshape(2, KC + 2, ld)[0]
+    cellp = small[2 * (KC + 2) * ld:2 * (KC + 2) * ld + 2 * Nc * (KGp + 2)].reshape(2, Nc, KGp + 2)[0]
+    cellm = mode.upper() == 'CELL'
+    if Kc > 0:
+        close(10 * ev[:Kc, :Ng], grads['Wc_loc'], 'Wc')
+    if 'intercept' in grads:
+        close(10 * (cellp[:, KGp] if cellm else ev[KC, :Ng]), grads['intercept'].reshape(-1), 'intercept')
+    if 'sigma_log' in grads:
+        close(10 * (cellp[:, KGp + 1] if cellm else ev[KC + 1, :Ng]), grads['sigma_log'].reshape(-1), 'sigma_log')
+    if Kg > 0:
+        close(10 * cellp[:, :Kg], grads['Wg_loc'], 'Wg')
+
+
+def test_marginlik_fit_matches_oracle():
+    """BRIE2.fit(target='marginLik') end to end: schedule, per-step loss, loss_gene (prior samples,
+    MC_size 1 per evaluation) against the float32 oracle with the device's noise."""
+    from brie_b200.models import BRIE2
+    from util import device_eps_provider as dep
+    Nc, Ng, seed = 80, 45, 3
+    data, effLen, Xc, _ = make_problem(Nc, Ng, 1, 0, True, 3, seed=5)
+    add_pseudo_count(data, np.float32(0.01))
+    kw = dict(min_iter=240, max_iter=740, add_iter=500, MC_size=5)
+    m = BRIE2(Nc=Nc, Ng=Ng, Kc=1, Kg=0, effLen=effLen, intercept=None, intercept_mode='gene', seed=seed)
+    losses = m.fit([x.copy() for x in data], Xc=Xc, target="marginLik", n_eval=20, verbose=False, **kw)
+    om = OracleBRIE2(Nc, Ng, 1, 0, effLen, None, 'gene', None, dtype=np.float32, seed=seed)
+    ref = om.fit([x.copy() for x in data], Xc=Xc, target="marginLik", n_eval=20,
+                 eps_provider=dep(seed, 0, Nc, Ng), **kw)
+    assert m.n_iter == om.n_iter and losses.shape == ref.shape
+    assert np.abs(losses - ref).max() <= 1e-4 * np.abs(ref).max()
+    assert np.abs(m.loss_gene.numpy() - om.loss_gene).max() <= 1e-4 * np.abs(om.loss_gene).max()
+    assert np.abs(m.Wc_loc.numpy() - om.p['Wc_loc']).max() < 2e-3
+    assert np.abs(m.sigma.numpy() - om.sigma).max() < 2e-3
+    assert np.abs(m.intercept.numpy() - om.p['intercept']).max() < 2e-3
+    assert np.abs(m.Z_loc.numpy() - om.p['Z_loc']).max() < 2e-5      # variational parameters stay at their init

@@ -26,12 +26,12 @@ def test_library_exports_every_declared_symbol(lib):
     for name in sorted(declared):
         assert hasattr(lib, name), "missing export: " + name
     assert declared == set(_lib.SYMBOLS), "ctypes table and header disagree"
-    assert lib.brie_abi_version() == 1
+    assert lib.brie_abi_version() == _lib.ABI_VERSION
 
 
 def test_struct_layout_matches_header():
     from brie_b200 import _lib
-    assert C.sizeof(_lib.FitDesc) == 4 * 8 + 8 + 10 * 4 + 32 * 4 + 32 * 4
+    assert C.sizeof(_lib.FitDesc) == 4 * 8 + 8 + 12 * 4 + 32 * 4 + 32 * 4
     assert C.sizeof(_lib.FitBuffers) == 17 * 8
     assert C.sizeof(_lib.FitSizes) == 2 * 8 + 4 * 4
 

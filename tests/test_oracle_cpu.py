@@ -46,6 +46,38 @@ CASES = [('gene', True, 3, 2, 0, None, None), ('gene', False, 2, 1, 3, None, Non
 
 
 @pytest.mark.parametrize("mode,eff,n_layers,Kc,Kg,intercept,sigma", CASES)
+def test_marginlik_gradients_match_autograd(mode, eff, n_layers, Kc, Kg, intercept, sigma):
+    """target='marginLik' (model_TFProb.py:156-157, 188-189, 202-205): prior-sampled
+    log-mean-exp objective; analytic gradients of the prior's parameters vs autograd."""
+    Nc, Ng, S = 30, 22, 4
+    data, effLen, Xc, Xg = make_problem(Nc, Ng, Kc, Kg, eff, n_layers)
+    add_pseudo_count(data, np.float32(0.01))
+    om = OracleBRIE2(Nc, Ng, Kc, Kg, effLen, intercept, mode, sigma, dtype=np.float64, seed=7)
+    om.Xc, om.Xg = Xc.astype(np.float64), Xg.astype(np.float64)
+    eps = om.eps(px.PHASE_TRAIN, 3, S)
+    loss, lg, grads = om.loss_and_grads(data, eps, target="marginLik")
+    ishape = (Nc, 1) if mode == 'cell' else (1, Ng)
+    init = OracleInit(Nc, Ng, Kc, Kg, ishape, ishape, intercept, sigma, seed=7)
+    em = EagerBRIE2(Nc, Ng, Kc, Kg, effLen, intercept, mode, sigma, init, torch.float64)
+    em.set_design(Xc, Xg)
+    cl = [torch.tensor(x, dtype=torch.float64) for x in data]
+    te = torch.tensor(eps, dtype=torch.float64)
+    tl = em.get_loss(cl, te, target="marginLik")
+    vs = em.variables("marginLik")
+    assert 'Z_loc' not in vs and sorted(vs) == sorted(grads)
+    assert abs(loss - float(tl.detach())) < 1e-9 * abs(loss)
+    if vs:
+        gs = dict(zip(vs.keys(), torch.autograd.grad(tl, list(vs.values()))))
+        for k in gs:
+            assert np.abs(grads[k] - gs[k].numpy()).max() < 1e-9 * max(1, np.abs(grads[k]).max()), k
+    assert np.abs(lg - em.get_loss(cl, te, axis=0, target="marginLik").detach().numpy()).max() < 1e-9 * np.abs(lg).max()
+    # an element without reads contributes exactly nothing (log-mean-exp of zeros)
+    zero = [np.zeros_like(x) for x in data]
+    l0, lg0, g0 = om.loss_and_grads(zero, eps, target="marginLik")
+    assert l0 == 0 and not lg0.any() and all(not np.asarray(v).any() for v in g0.values())
+
+
+@pytest.mark.parametrize("mode,eff,n_layers,Kc,Kg,intercept,sigma", CASES)
 def test_analytic_gradients_match_autograd(mode, eff, n_layers, Kc, Kg, intercept, sigma):
     Nc, Ng, S = 30, 22, 3
     data, effLen, Xc, Xg = make_problem(Nc, Ng, Kc, Kg, eff, n_layers)
