@@ -12,6 +12,21 @@ from brie_b200.utils.base_utils import match
 from brie_b200.utils.preprocessing import filter_genes
 
 
+def _init_distributed():
+    """(rank, world).  Under torchrun (WORLD_SIZE > 1 in the environment) join the NCCL process
+    group with this rank's GPU as the current device; otherwise a single process."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return dist.get_rank(), world
+
+
 def _read_table(path):
     delim = "," if path.endswith('csv') or path.endswith('csv.gz') else "\t"
     return np.genfromtxt(path, dtype="str", delimiter=delim)
@@ -24,7 +39,12 @@ def quant(in_file, cell_file=None, gene_file=None, out_file=None,
           min_iter=5000, max_iter=20000, MC_size=1, batch_size=500000,
           pseudo_count=0.01, base_mode='full', seed=0):
     """CLI driver (quant.py:13-130).  `nproc` is accepted for compatibility (host threads are
-    not on the hot path any more); `seed` keys the counter-based noise (new, default 0)."""
+    not on the hot path any more); `seed` keys the counter-based noise (new, default 0).
+
+    Multi-GPU: launch one process per GPU (`python -m torch.distributed.run --nproc-per-node N
+    -m brie_b200.bin.quant ...`); every rank reads the input, fits its own event shard
+    (fitBRIE) and rank 0 writes the outputs."""
+    rank, world = _init_distributed()
     if out_file is None:
         print("No given out_file, use the dir for input file.")
         out_file = os.path.dirname(os.path.abspath(in_file)) + "/brie_quant.h5ad"
@@ -80,6 +100,8 @@ def quant(in_file, cell_file=None, gene_file=None, out_file=None,
     adata.uns['Xc_ids'] = Xc_ids
     adata.uns['Xg_ids'] = Xg_ids
 
+    if rank != 0:                                                # every rank holds the full result; one writes it
+        return adata
     if hasattr(adata, 'write_npz') and not io_utils._anndata:    # no anndata/h5py here: npz container
         out_file = ".".join(out_file.split('.')[:-1]) + '.npz' if out_file.endswith('.h5ad') else out_file
         adata.write_npz(out_file)
@@ -163,6 +185,11 @@ def main():
           options.min_uniq_count, options.min_cell, options.min_MIF,
           options.min_iter, options.max_iter, options.MC_size,
           options.batch_size, options.pseudo_count, options.test_base, options.seed)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.barrier()
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -131,9 +131,10 @@ class FitEngine:
         self.Xg = torch.from_numpy(xg[:, :max(self.Kg, 1)]).contiguous().to(dev)
 
         M = self.M
-        self.Z_loc = torch.zeros((M, self.Nc, ld), dtype=f32, device=dev)
-        self.Z_std_log = torch.zeros((M, self.Nc, ld), dtype=f32, device=dev)
-        self.adam_Z = torch.zeros((4, M, self.Nc, ld), dtype=f32, device=dev)
+        # init_params fills Z_loc / Z_std_log completely and begin_stage clears the Adam moments
+        self.Z_loc = torch.empty((M, self.Nc, ld), dtype=f32, device=dev)
+        self.Z_std_log = torch.empty((M, self.Nc, ld), dtype=f32, device=dev)
+        self.adam_Z = torch.empty((4, M, self.Nc, ld), dtype=f32, device=dev)
         self.Wc = torch.zeros((M, max(self.Kc, 1), ld), dtype=f32, device=dev)
         nsmall = self.Nc if self.cell_mode else ld
         self.intercept = torch.zeros((M, nsmall), dtype=f32, device=dev)

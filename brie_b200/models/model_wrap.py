@@ -113,6 +113,21 @@ def _rv_from_engine(eng, m, Xc_model, Xg, intercept_mode):
     return rv
 
 
+def _host_pseudo_count_inplace(data, pseudo_count):
+    """Side effect of model_wrap.py:113-117 on the caller's dense arrays: where c1 + c2 > 0 add the
+    pseudo-count to c1 and c2 in place.  (The fit itself reads the device tiles.)"""
+    try:
+        import torch
+        t0, t1 = torch.from_numpy(data[0]), torch.from_numpy(data[1])     # views of the caller's memory
+        inc = ((t0 + t1) > 0).to(t0.dtype).mul_(pseudo_count)
+        t0.add_(inc)
+        t1.add_(inc.to(t1.dtype))
+    except (TypeError, ValueError, RuntimeError):      # read-only / unsupported dtype: numpy semantics
+        idx = data[0] + data[1] > 0
+        for i in range(2):
+            data[i][idx] = data[i][idx] + pseudo_count
+
+
 def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
                     intercept_mode='gene', LRT_index=None, pseudo_count=0.01,
                     sigma=None, base_mode='full', tau_prior=[3, 27], **keyargs):
@@ -139,8 +154,19 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     for k in ('optimizer', 'learn_rate', 'verbose'):                # accepted and ignored (:214-237)
         keyargs.pop(k, None)
 
+    import os
+    import time
     import torch
     from .. import ingest
+    timing = {} if os.environ.get("BRIE_TIMING") else None         # phase wall times (diagnostic; syncs the device)
+
+    def _tick(name, t0):
+        if timing is not None:
+            torch.cuda.synchronize()
+            timing[name] = timing.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
+
+    t_ph = time.perf_counter()
     if not torch.cuda.is_available():
         raise RuntimeError("brie_b200: no CUDA device (there is no CPU fallback)")
     dev = torch.device(device if device is not None else "cuda")
@@ -148,24 +174,18 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
         dev = torch.device("cuda", torch.cuda.current_device())
     Nc, Ng = data[0].shape
     print("[BRIE2] adding pseudo_count:", pseudo_count)
-    if any(issparse(d) or (torch.is_tensor(d) and d.is_cuda) for d in data):
-        # sparse layers are NOT densified on the host (:108-111): the stored counts go to the
-        # device, are scattered there and get the pseudo-count there (:113-117)
-        tiles, h2d_bytes = [], 0
-        for d in data:
-            t, nb = ingest.layer_to_device(d, 0, Ng, dev)
-            tiles.append(t)
-            h2d_bytes += nb
-        ingest.add_pseudo_count(tiles, pseudo_count)
-    else:
-        idx = data[0] + data[1] > 0                                 # :113-117 (in place, like the reference)
-        for i in range(2):
-            data[i][idx] = data[i][idx] + pseudo_count
-        tiles, h2d_bytes = [], 0
-        for d in data:
-            t, nb = ingest.layer_to_device(d, 0, Ng, dev)
-            tiles.append(t)
-            h2d_bytes += nb
+    # The stored counts go to the device as they are (sparse layers are NOT densified on the
+    # host, :108-111), are scattered there and get the pseudo-count there (:113-117).
+    tiles, h2d_bytes = [], 0
+    for d in data:
+        t, nb = ingest.layer_to_device(d, 0, Ng, dev)
+        tiles.append(t)
+        h2d_bytes += nb
+    ingest.add_pseudo_count(tiles, pseudo_count)
+    # the reference also leaves the pseudo-count in the caller's dense arrays (in-place add, :115-117)
+    if all(isinstance(d, np.ndarray) for d in data[:2]):
+        _host_pseudo_count_inplace(data, pseudo_count)
+    t_ph = _tick("pseudo_count+ingest", t_ph)
     if Xc is None:
         Xc = np.ones((Nc, 0), np.float32)
     if Xg is None:
@@ -218,14 +238,18 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
                              intercept_mode=intercept_mode, **common)]
         where = [(0, i) for i in range(T + 1)]
         inits = [init_objs]
+    t_ph = _tick("engine_setup", t_ph)
     for eng, io in zip(engines, inits):
         eng.fit(n_eval=n_eval, init_objs=io, **keyargs)             # :144, :180
+    t_ph = _tick("fit", t_ph)
 
     e0, m0 = engines[where[0][0]], where[0][1]
     brie_results = _rv_from_engine(e0, m0, Xc[:, base_cols], Xg, intercept_mode)   # :146
     brie_results.n_iter = np.stack([engines[w[0]].n_iter[w[1]] for w in where], axis=0)  # (1+T, groups)
     brie_results.launch_count = sum(e.launch_count for e in engines)
     brie_results.h2d_bytes = h2d_bytes
+    t_ph = _tick("posterior+d2h", t_ph)
+    brie_results.timing = timing
     if T == 0:                                                      # :152-153
         return brie_results
 

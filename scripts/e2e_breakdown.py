@@ -1,30 +1,42 @@
-"""Phase timing of a full C2 fit (diagnostic)."""
-import sys, os, time
+"""Phase timing of the public-API C2 fit (bench.py's e2e leg) and of its engine internals (diagnostic)."""
+import contextlib, io, os, sys, time
+os.environ["BRIE_TIMING"] = "1"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import bench
-from brie_b200.engine import FitEngine, LEARNING_RATES
+from brie_b200.engine import FitEngine
+from brie_b200.models import fit_BRIE_matrix
 
+orig_fit = FitEngine.fit
+
+
+def timed_fit(self, *a, **k):
+    def T():
+        torch.cuda.synchronize(); return time.perf_counter()
+    ev, rs = self.eval_loss_gene, self.run_steps
+    acc = {"eval": 0.0, "steps": 0.0, "nsteps": 0, "loss_steps": 0}
+
+    def ev2(*aa, **kk):
+        t = T(); r = ev(*aa, **kk); acc["eval"] += T() - t; return r
+
+    def rs2(n, slot=-1):
+        t = T(); r = rs(n, slot); acc["steps"] += T() - t; acc["nsteps"] += n
+        acc["loss_steps"] += n if slot >= 0 else 0
+        return r
+    self.eval_loss_gene, self.run_steps = ev2, rs2
+    t0 = T(); out = orig_fit(self, *a, **k); tot = T() - t0
+    print("engine.fit %.3f s: steps %.3f s (%d launches, %d with loss trace), loss_gene eval %.3f s, host logic %.3f s"
+          % (tot, acc["steps"], acc["nsteps"], acc["loss_steps"], acc["eval"], tot - acc["steps"] - acc["eval"]))
+    return out
+
+
+FitEngine.fit = timed_fit
 layers, effLen, Xc = bench.make_c2(1)
-idx = layers[0] + layers[1] > 0
-for i in range(2):
-    layers[i][idx] += np.float32(0.01)
-def T():
-    torch.cuda.synchronize(); return time.perf_counter()
-t0 = T()
-eng = FitEngine(layers, effLen=effLen, Xc=Xc, masks=[[0], []], model_ids=[0, 1], MC_size=3, seed=7,
-                group_size=100, trace_cap=833)
-t1 = T(); print("engine build + H2D %.3f s" % (t1 - t0))
-eng.init_params(); t2 = T(); print("init %.3f" % (t2 - t1))
-for i, lr in enumerate(LEARNING_RATES):
-    eng.begin_stage(lr); eng.run_steps(833, 0 if i == 5 else -1)
-    t3 = T(); print("stage %d: %.3f s  (%.4f ms/step)" % (i, t3 - t2, (t3 - t2) / 833 * 1e3)); t2 = t3
-tr = eng.group_trace(833); t4 = T(); print("group_trace %.3f" % (t4 - t3))
-for frac in (1.0, 0.5, 0.1):
-    act = np.zeros((2, 50), bool); act[:, :int(50 * frac)] = True
-    eng.set_active_groups(act); t5 = T()
-    eng.run_steps(500, 0); t6 = T(); print("extension active %.2f: %.3f s (%.4f ms/step)" % (frac, t6 - t5, (t6 - t5) / 500 * 1e3))
-eng.set_active_groups(np.ones((2, 50), bool))
-t7 = T(); lg = eng.eval_loss_gene(500); t8 = T(); print("eval_loss_gene(500) %.3f s" % (t8 - t7))
-post = [t.cpu().numpy() for t in eng.posterior(0)]; z = eng.Z_loc[0, :, :5000].cpu().numpy(); t9 = T()
-print("posterior + D2H %.3f s" % (t9 - t8))
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+with contextlib.redirect_stdout(io.StringIO()) as buf:
+    res = fit_BRIE_matrix(layers, Xc=Xc, effLen=effLen, intercept=None, intercept_mode='gene', LRT_index=None,
+                          min_iter=5000, max_iter=20000, MC_size=3, group_size=100, seed=7)
+torch.cuda.synchronize()
+print(buf.getvalue().strip().splitlines()[-1])
+print("fit_BRIE_matrix total %.3f s" % (time.perf_counter() - t0), res.timing)

@@ -80,3 +80,47 @@ def test_sharded_fitBRIE_matches_single_gpu(tmp_path):
         tol_med = 1e-5 if k == 'Psi' else 2e-3
         assert np.median(d) < tol_med and np.quantile(d, 0.99) < 1e-2 and d.max() < 5e-2, k
     assert np.abs(b1['lg'] - b2['lg']).max() <= 1e-3 * np.abs(b1['lg']).max()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_brie_quant_cli_under_torchrun(tmp_path):
+    """`torchrun --nproc-per-node 2 -m brie_b200.bin.quant ...`: ranks shard the events, rank 0
+    writes the same container and TSV as the single-process run (out_dir memmaps shared)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import make_lrt_problem
+    from brie_b200.utils import io_utils
+    from brie_b200.utils.anndata_lite import AnnDataLite
+    Nc, Ng = 120, 90
+    data, effLen, Xc, _ = make_lrt_problem(Nc, Ng, seed=21)
+    eff3 = np.zeros((Ng, 2, 3), np.float32)
+    eff3[:, 0, :], eff3[:, 1, :] = effLen[:, :3], effLen[:, 3:]
+    cells = ["cell%03d" % i for i in range(Nc)]
+    inp = str(tmp_path / "counts.npz")
+    io_utils.write_npz_counts(inp, {'isoform1': data[0], 'isoform2': data[1], 'ambiguous': data[2]}, eff3, cells,
+                              ["g%03d" % i for i in range(Ng)])
+    cf = tmp_path / "cells.tsv"
+    with open(cf, "w") as f:
+        f.write("cellID\tgroup\n")
+        for i in range(Nc):
+            f.write("%s\t%d\n" % (cells[i], int(Xc[i, 0])))
+    outs = {}
+    for world in (1, 2):
+        out = str(tmp_path / ("w%d" % world) / "brie_quant.npz")
+        args = ["-m", "brie_b200.bin.quant", "-i", inp, "-c", str(cf), "-o", out, "--LRTindex", "All",
+                "--interceptMode", "gene", "--minIter", "300", "--maxIter", "800", "--MCsize", "2",
+                "--batchSize", str(Nc * 16), "--minCount", "10", "--minUniqCount", "5", "--minCell", "5"]
+        if world == 1:
+            cmd = [sys.executable] + args
+        else:
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                   "--master-addr", "127.0.0.1", "--master-port", "29657"] + args
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT,
+                           env=dict(os.environ, PYTHONPATH=ROOT))
+        assert p.returncode == 0, p.stderr[-3000:]
+        outs[world] = (AnnDataLite.read_npz(out), open(out.replace(".npz", ".brie_ident.tsv")).read())
+    a1, a2 = outs[1][0], outs[2][0]
+    assert a1.shape == a2.shape
+    assert np.abs(a1.layers['Psi'] - a2.layers['Psi']).max() < 1e-4
+    assert np.array_equal(a1.varm['fdr'] < 0.05, a2.varm['fdr'] < 0.05)
+    assert np.abs(a1.varm['ELBO_gain'] - a2.varm['ELBO_gain']).max() < 1e-3
+    assert outs[1][1].splitlines()[0] == outs[2][1].splitlines()[0]
