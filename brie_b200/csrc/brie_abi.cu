@@ -64,11 +64,11 @@ cudaError_t launch_step(const StepArgs& a, dim3 grid, cudaStream_t s) {
   static bool configured = false;  // per instantiation: opt in to > 48 KB dynamic shared memory
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(elbo_step_kernel<KC, KG, CELL, LOSS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, step_smem_bytes(KC));
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, step_smem_bytes(KC, KG, CELL, LOSS));
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  elbo_step_kernel<KC, KG, CELL, LOSS><<<grid, kThreads, step_smem_bytes(KC), s>>>(a);
+  elbo_step_kernel<KC, KG, CELL, LOSS><<<grid, kThreads, step_smem_bytes(KC, KG, CELL, LOSS), s>>>(a);
   return cudaGetLastError();
 }
 

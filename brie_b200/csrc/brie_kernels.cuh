@@ -222,8 +222,20 @@ constexpr int kQueueFields = 6;   // mu, s, c1, c2, c3, column  ->  results over
 constexpr int kRingArrays = 9;    // Z_loc, Z_std_log, c1, c2, c3, m_loc, v_loc, m_std, v_std
 constexpr int kRingStages = 2;
 __host__ __device__ constexpr int step_tile_cols(int KC) { return 32 * step_epl(KC); }
-__host__ __device__ constexpr int step_smem_bytes(int KC) {
-  return (kWarps * kRingStages * kRingArrays + kWarps * kQueueFields + 6) * step_tile_cols(KC) * 4;
+// Per-event constants of a column tile (Wc rows, Xg columns, intercept, sigma_log, 1/sigma^2) stay in
+// registers for narrow designs; wider ones keep them in shared memory and re-read them every row, so
+// they are not live across the Monte-Carlo phase (no spills).  Measured on one box (profiles/
+// r1_ab_smem_consts.md): C3 with loss trace +11 %, C4 +10 % / +23 %, Kc 15 +9 %; only Kc <= 4 without
+// gene features and without the loss trace is faster from registers (C3: 4 %).
+__host__ __device__ constexpr bool step_consts_in_smem(int KC, int KG, bool LOSS) {
+  return KC + KG >= 3 && !(KG == 0 && KC <= 4 && !LOSS);
+}
+__host__ __device__ constexpr int step_n_consts(int KC, int KG, bool CELL, bool LOSS) {
+  return step_consts_in_smem(KC, KG, LOSS) ? KC + KG + (CELL ? 0 : 3) : 0;
+}
+__host__ __device__ constexpr int step_smem_bytes(int KC, int KG, bool CELL, bool LOSS) {
+  return (kWarps * kRingStages * kRingArrays + kWarps * kQueueFields + 6 + step_n_consts(KC, KG, CELL, LOSS)) *
+         step_tile_cols(KC) * 4;
 }
 
 template <int KC, int KG, bool CELL, bool LOSS>
@@ -233,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   constexpr int NCELL = T::NCELL;
   constexpr int EPL = step_epl(KC);
   constexpr int TC = 32 * EPL;              // events per warp row segment (column tile)
+  constexpr bool kSm = step_consts_in_smem(KC, KG, LOSS);
   using Vec = typename LaneVec<EPL>::type;
   const int m = blockIdx.x;
   if (!((a.model_mask >> m) & 1u)) return;
@@ -256,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
                                                  warp * kQueueFields * TC);
   float(*s_L)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * kRingArrays * TC +
                                                    kWarps * kQueueFields * TC);
+  float(*s_k)[TC] = s_L + 6;                // kSm: rows Wc[0..KC), Xg[0..KG), then (gene mode) b, tau, 1/sigma^2
 
   const int64_t row_begin = (int64_t)chunk * a.rows_per_cta;
   const int64_t row_end = min(row_begin + (int64_t)a.rows_per_cta, a.Nc);
@@ -293,6 +307,19 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       s_L[3][threadIdx.x] = logf(l1); s_L[4][threadIdx.x] = logf(l2);
       s_L[5][threadIdx.x] = a.eff ? logf(l3) : 0.f;
     }
+    if (kSm) {
+      const bool okc = g < a.ld;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) s_k[k][threadIdx.x] = okc ? a.Wc[((int64_t)m * KC + k) * a.ld + g] : 0.f;
+#pragma unroll
+      for (int k = 0; k < KG; ++k) s_k[KC + k][threadIdx.x] = g < a.Ng ? a.Xg[g * KG + k] : 0.f;
+      if (!CELL) {
+        const float t = okc ? a.tau[(int64_t)m * a.ld + g] : 0.f;
+        s_k[KC + KG][threadIdx.x] = okc ? a.b[(int64_t)m * a.ld + g] : 0.f;
+        s_k[KC + KG + 1][threadIdx.x] = t;
+        s_k[KC + KG + 2][threadIdx.x] = fast_exp(-2.0f * t);
+      }
+    }
   }
   float wc[KC > 0 ? KC : 1][EPL];
   float xg[KG > 0 ? KG : 1][EPL];
@@ -309,7 +336,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   for (int k = 0; k < (KG > 0 ? KG : 1); ++k)
 #pragma unroll
     for (int j = 0; j < EPL; ++j) xg[k][j] = 0.f;
-  if (in_ld) {
+  if (in_ld && !kSm) {
 #pragma unroll
     for (int k = 0; k < KC; ++k)
       vec_get<EPL>(*reinterpret_cast<const Vec*>(a.Wc + ((int64_t)m * KC + k) * a.ld + g0), wc[k]);
@@ -325,7 +352,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       for (int j = 0; j < EPL; ++j) is2[j] = fast_exp(-2.0f * tau[j]);
     }
   }
-  __syncthreads();  // s_L visible
+  __syncthreads();  // s_L, s_k visible
 
   float acc[NEV > 0 ? NEV : 1][EPL];
 #pragma unroll
@@ -378,6 +405,17 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     for (int i = 0; i < (NCELL > 0 ? NCELL : 1); ++i) cacc[i] = 0.f;
 
     // ---- phase A: KL terms, shared-parameter accumulators, non-zero detection ----
+    if (kSm) {  // this row's copy of the tile constants (dead again before the Monte-Carlo phase)
+#pragma unroll
+      for (int k = 0; k < KC; ++k) vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[k][lane * EPL]), wc[k]);
+#pragma unroll
+      for (int k = 0; k < KG; ++k) vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + k][lane * EPL]), xg[k]);
+      if (!CELL) {
+        vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + KG][lane * EPL]), bb);
+        vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + KG + 1][lane * EPL]), tau);
+        vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + KG + 2][lane * EPL]), is2);
+      }
+    }
     float gmu[EPL], glam[EPL];
     uint32_t nz = 0;
 #pragma unroll
