@@ -279,8 +279,11 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 
   // ring producer: this lane's EPL-float column of each array, one commit group per row
   const uint32_t ring_lane = (uint32_t)__cvta_generic_to_shared(s_ring) + lane * (EPL * 4);
+  // Lanes whose events are all frozen (converged reference batches) copy nothing: their ring slots are
+  // zero-filled, they compute on zeros and store nothing, so a partly active tile only pays for the
+  // 32-byte sectors that hold active events.
   auto issue_row = [&](int64_t row, int stage) {
-    const bool ok = in_ld && row < row_end;
+    const bool ok = act != 0 && row < row_end;
     const int64_t off = ok ? row * a.ld + g0 : 0;
     const int64_t moff = ok ? (int64_t)m * plane + off : 0;
     const uint32_t dst = ring_lane + stage * (kRingArrays * TC * 4);
