@@ -32,6 +32,30 @@ def fdr_bh(pvals):
     return out
 
 
+def fdr_by_group(pval, group_size=None, event_offset=0):
+    """BH-FDR of each test column within the reference's multiple-testing scope.
+
+    The reference corrects inside each fit_BRIE_matrix call (model_wrap.py:193-196), i.e. per
+    event batch of ceil(batch_size / n_cells) events when called from fitBRIE (:241-256).
+    Events fitted together here keep that scope per convergence group: `group_size` events per
+    group, groups counted from global event 0 (`event_offset` = global index of row 0).
+    Pinned on the reference's published result tables (tests/golden/published_lrt.npz)."""
+    pval = np.asarray(pval)
+    Ng = pval.shape[0]
+    fdr = np.zeros(pval.shape)
+    if group_size is None:
+        bounds = [(0, Ng)]
+    else:
+        first = event_offset // group_size
+        last = (event_offset + Ng - 1) // group_size
+        bounds = [(max(g * group_size - event_offset, 0), min((g + 1) * group_size - event_offset, Ng))
+                  for g in range(first, last + 1)]
+    for lo, hi in bounds:
+        for i in range(fdr.shape[1]):
+            fdr[lo:hi, i] = fdr_bh(pval[lo:hi, i])
+    return fdr
+
+
 class BRIE_RV():
     """Return value object for BRIE2 model (model_wrap.py:15-76)."""
 
@@ -265,19 +289,7 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
             brie_results.cell_coeff = np.append(brie_results.cell_coeff, wc_last, axis=0)  # :186-187
     brie_results.ELBO_gain = ELBO_gain                              # H1 vs NUll
     brie_results.pval = chi2.sf(2 * ELBO_gain, df=1)                # :190
-    # The reference corrects for multiple testing inside each fit_BRIE_matrix call, i.e. per event
-    # batch when called from fitBRIE (:193-196 under :245-256): keep that scope per convergence group.
-    fdr = np.zeros(ELBO_gain.shape)
-    if group_size is None:
-        bounds = [(0, Ng)]
-    else:
-        first = event_offset // group_size
-        last = (event_offset + Ng - 1) // group_size
-        bounds = [(max(g * group_size - event_offset, 0), min((g + 1) * group_size - event_offset, Ng))
-                  for g in range(first, last + 1)]
-    for lo, hi in bounds:
-        for i in range(fdr.shape[1]):
-            fdr[lo:hi, i] = fdr_bh(brie_results.pval[lo:hi, i])
+    fdr = fdr_by_group(brie_results.pval, group_size, event_offset)
     brie_results.fdr = fdr
     return brie_results
 

@@ -67,24 +67,20 @@ def write_npz_counts(path, layers, effLen_tensor, cell_ids, gene_ids):
 
 
 def dump_results(adata):
-    """Result table of detected splicing phenotypes (io_utils.py:163-199), including the
-    reference's column naming (`_ceoff`) and its positional indexing of cell_coeff."""
-    X = adata.X
-    df = adata.var[['n_counts', 'n_counts_uniq']].copy()
-    df['n_counts'] = df['n_counts'].astype(int)
-    df['n_counts_uniq'] = df['n_counts_uniq'].astype(int)
-    df['cdr'] = np.asarray((X > 0).mean(0)).reshape(-1)
-    df['intercept'] = adata.varm['intercept'][:, 0] if 'intercept' in adata.varm else [None] * adata.shape[1]
-    df['sigma'] = adata.varm['sigma'][:, 0] if 'sigma' in adata.varm else [None] * adata.shape[1]
-    LRT_index = adata.uns['brie_param']['LRT_index'] if 'brie_param' in adata.uns else []
-    for i in range(len(LRT_index)):
-        _idx = LRT_index[i]
-        if 'Xc_ids' in adata.uns and adata.uns['Xc_ids'] is not None:
-            name = adata.uns['Xc_ids'][_idx]
-        else:
-            name = 'X%d' % i
-        df[name + '_ceoff'] = adata.varm['cell_coeff'][:, i]
-        df[name + '_ELBO_gain'] = adata.varm['ELBO_gain'][:, i]
-        df[name + '_pval'] = adata.varm['pval'][:, i]
-        df[name + '_FDR'] = adata.varm['fdr'][:, i]
-    return df
+    """Per-event result table of the detected splicing phenotypes, the table brie-quant writes as
+    <out>.brie_ident.tsv (io_utils.py:163-199; header pinned on the published tables in
+    tests/golden/published_lrt.npz).  Keeps the reference's `_ceoff` spelling and its indexing of
+    cell_coeff by loop position rather than by LRT_index."""
+    n_events = adata.shape[1]
+    table = adata.var[['n_counts', 'n_counts_uniq']].astype(int)
+    table['cdr'] = np.asarray((adata.X > 0).mean(0)).reshape(-1)
+    for key in ('intercept', 'sigma'):
+        table[key] = adata.varm[key][:, 0] if key in adata.varm else [None] * n_events
+    tested = adata.uns['brie_param']['LRT_index'] if 'brie_param' in adata.uns else []
+    names = adata.uns['Xc_ids'] if 'Xc_ids' in adata.uns else None
+    for pos, feature in enumerate(tested):
+        label = names[feature] if names is not None else 'X%d' % pos
+        for suffix, source in (('_ceoff', 'cell_coeff'), ('_ELBO_gain', 'ELBO_gain'),
+                               ('_pval', 'pval'), ('_FDR', 'fdr')):
+            table[label + suffix] = adata.varm[source][:, pos]
+    return table

@@ -218,3 +218,49 @@ print("rank", r, "ok")
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.count("ok") == 2
+
+@pytest.mark.parametrize("table", ["msEAE", "scNT", "dentate"])
+def test_fdr_by_group_reproduces_published_reference_tables(table):
+    """The product's multiple-testing scope (fdr_by_group over convergence groups of
+    ceil(batch_size / n_cells) events, any chunking / sharding of the events) reproduces the FDR
+    columns of the reference's published result tables (tests/golden/published_lrt.npz)."""
+    from brie_b200.models.model_wrap import fdr_by_group
+    from brie_b200.sharding import event_shards
+    pub = np.load(os.path.join(ROOT, "tests", "golden", "published_lrt.npz"), allow_pickle=True)
+    pval, fdr = pub[table + "_pval"], pub[table + "_fdr"]
+    n_gene = int(np.ceil(int(pub[table + "_batch_size"]) / int(pub[table + "_n_cells"])))
+    Ng = len(pval)
+    got = fdr_by_group(pval, n_gene, 0)
+    assert np.all(np.abs(got - fdr) <= 2e-3 * fdr)
+    # fitted as 3 rank shards (group-aligned), each in chunks of 4 groups, as fitBRIE does
+    parts = []
+    for lo, hi in event_shards(Ng, 3, n_gene):
+        for e0 in range(lo, hi, 4 * n_gene):
+            e1 = min(e0 + 4 * n_gene, hi)
+            parts.append(fdr_by_group(pval[e0:e1], n_gene, e0))
+    assert np.array_equal(np.concatenate(parts, 0), got)
+    assert not np.allclose(fdr_by_group(pval, None), fdr, rtol=1e-2)
+
+
+def test_dump_results_header_matches_published_table():
+    """Column names and order of the result table (io_utils.py:163-199) against the header of the
+    reference's published msEAE table, including the '_ceoff' spelling."""
+    import pandas as pd
+    from brie_b200.utils.anndata_lite import AnnDataLite
+    from brie_b200.utils.io_utils import dump_results
+    pub = np.load(os.path.join(ROOT, "tests", "golden", "published_lrt.npz"), allow_pickle=True)
+    rng = np.random.default_rng(0)
+    X = rng.poisson(0.3, (6, 4)).astype(np.float32)
+    ad = AnnDataLite(X=X, var=pd.DataFrame({'n_counts': X.sum(0), 'n_counts_uniq': X.sum(0)},
+                                           index=pd.Index(list("abcd"), name="GeneID")))
+    ad.varm['intercept'] = rng.normal(size=(4, 1))
+    ad.varm['sigma'] = rng.uniform(size=(4, 1))
+    for k in ('cell_coeff', 'ELBO_gain', 'pval', 'fdr'):
+        ad.varm[k] = rng.uniform(size=(4, 2 if k == 'cell_coeff' else 1))
+    ad.uns['brie_param'] = {'LRT_index': [0]}
+    ad.uns['Xc_ids'] = ['isEAE', 'isCD1']
+    df = dump_results(ad)
+    assert [df.index.name] + list(df.columns) == list(pub['msEAE_columns'])
+    line = df.to_csv(sep='\t', float_format='%.3e').splitlines()[1].split('\t')
+    assert len(line) == 10 and all('e' in v for v in line[3:])       # quant.py:129-130 format
+    assert np.allclose(df['cdr'].values, (X > 0).mean(0))

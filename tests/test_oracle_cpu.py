@@ -193,3 +193,28 @@ def test_oracle_float32_tracks_float64():
         out.append(om)
     assert np.abs(out[0].Psi - out[1].Psi).max() < 1e-3
     assert np.abs(out[0].loss_gene - out[1].loss_gene).max() <= 1e-4 * np.abs(out[1].loss_gene).max()
+
+PUB = np.load(os.path.join(os.path.dirname(__file__), "golden", "published_lrt.npz"), allow_pickle=True)
+
+
+@pytest.mark.parametrize("table", ["msEAE", "scNT", "dentate"])
+def test_published_reference_tables_pin_pval_and_fdr(table):
+    """Outputs of the reference itself (brie-tutorials/*/data/*.brie_ident.tsv, fixture made by
+    tests/golden/make_published_lrt.py): pval = chi2.sf(2*ELBO_gain, 1) (model_wrap.py:190) and the
+    FDR column = BH applied per fitBRIE batch of ceil(batch_size / n_cells) events (:193-196 under
+    :241-256).  Values are printed with 4 significant digits ('%.3e')."""
+    from scipy.stats import chi2
+    gain, pval, fdr = PUB[table + "_gain"], PUB[table + "_pval"], PUB[table + "_fdr"]
+    n_gene = int(np.ceil(int(PUB[table + "_batch_size"]) / int(PUB[table + "_n_cells"])))
+    # d ln p / d gain ~ -1, the printed gain is good to 5e-4 relative
+    p2 = chi2.sf(2 * gain, df=1)
+    assert np.all(np.abs(p2 - pval) <= pval * 1e-3 * (1 + np.abs(gain)))
+    assert np.all(pval[gain <= 0] == 1.0)
+    got = np.zeros_like(fdr)
+    for lo in range(0, len(fdr), n_gene):
+        for j in range(fdr.shape[1]):
+            got[lo:lo + n_gene, j] = fdr_bh(pval[lo:lo + n_gene, j])
+    assert np.all(np.abs(got - fdr) <= 2e-3 * fdr)
+    # the pin has teeth: one BH over the whole column does not reproduce the table
+    whole = np.stack([fdr_bh(pval[:, j]) for j in range(fdr.shape[1])], 1)
+    assert np.mean(np.abs(whole - fdr) > 1e-2 * fdr) > 0.3
