@@ -291,6 +291,18 @@ class FitEngine:
     def fit(self, min_iter=1000, max_iter=5000, add_iter=500, epsilon_conv=1e-2, n_eval=500,
             init_objs=None, do_init=True):
         """BRIE2.fit (model_TFProb.py:214-273) for all batched models at once."""
+        import os
+        import time
+        timed = bool(os.environ.get("BRIE_TIMING"))                  # diagnostic phase wall times (syncs the device)
+        self.phase_s = {}
+
+        def tick(name, t0):
+            if timed:
+                torch.cuda.synchronize(self.device)
+                self.phase_s[name] = self.phase_s.get(name, 0.0) + time.perf_counter() - t0
+            return time.perf_counter()
+
+        t_ph = time.perf_counter()
         n_stage = int(min_iter / 6)
         if max(n_stage, add_iter) > self.trace_cap:
             raise ValueError("trace_cap %d too small for %d-step stages" % (self.trace_cap, max(n_stage, add_iter)))
@@ -305,6 +317,7 @@ class FitEngine:
         else:
             tr = np.zeros((M, NG, 0), np.float32)
         traces = [[tr[m, g] for g in range(NG)] for m in range(M)]
+        t_ph = tick("fit.schedule", t_ph)
         n_iter = np.full((M, NG), min_iter, np.int64)                # :247
         d1 = int(min(50, add_iter / 2))
         d2 = d1 * 2
@@ -328,11 +341,13 @@ class FitEngine:
                         traces[m][g] = np.concatenate([traces[m][g], tr[m, g]])
                         n_iter[m, g] += add_iter
         self.set_active_groups(np.ones((M, NG), bool))
+        t_ph = tick("fit.extensions", t_ph)
         self.n_iter = n_iter
         self.traces = traces
         # BRIE_RV.concate appends the per-batch traces end to end (model_wrap.py:61)
         self.losses = [np.concatenate(traces[m]) if NG else np.zeros(0, np.float32) for m in range(M)]
         self.loss_gene = self.eval_loss_gene(n_eval)                 # :261-264
+        tick("fit.loss_gene", t_ph)
         return self.losses
 
     # ------------------------------------------------------------------ results

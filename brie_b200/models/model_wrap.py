@@ -7,6 +7,8 @@ model_wrap.py:156-187) run as one batched `FitEngine`, and the sequential event
 batches of `fitBRIE` (model_wrap.py:241-260) become convergence groups inside
 the same launches, so one pass over the counts serves all of them.
 """
+import time
+
 import numpy as np
 from scipy.stats import chi2
 
@@ -109,6 +111,9 @@ class BRIE_RV():
             self.ELBO_gain = np.append(self.ELBO_gain, new_RV.ELBO_gain, axis=0)
         if hasattr(new_RV, 'n_iter'):
             self.n_iter = np.append(self.n_iter, new_RV.n_iter, axis=1)
+        if getattr(self, 'timing', None) is not None and getattr(new_RV, 'timing', None) is not None:
+            for k, v in new_RV.timing.items():                      # BRIE_TIMING diagnostics add up over chunks
+                self.timing[k] = self.timing.get(k, 0.0) + v
 
 
 def concate(BRIE_RV_list):
@@ -266,6 +271,10 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     for eng, io in zip(engines, inits):
         eng.fit(n_eval=n_eval, init_objs=io, **keyargs)             # :144, :180
     t_ph = _tick("fit", t_ph)
+    if timing is not None:
+        for eng in engines:
+            for k, v in eng.phase_s.items():
+                timing[k] = timing.get(k, 0.0) + v
 
     e0, m0 = engines[where[0][0]], where[0][1]
     brie_results = _rv_from_engine(e0, m0, Xc[:, base_cols], Xg, intercept_mode)   # :146
@@ -328,6 +337,30 @@ def _merge_shared(parts):
     return out
 
 
+def _fit_signature(Nc, Ng, Xc, LRT_index, layer_keys, n_gene, world, intercept, intercept_mode, pseudo_count,
+                   sigma, base_mode, keyargs):
+    """What has to be equal for checkpointed event chunks to belong to the same fit."""
+    import hashlib
+    kw = {k: (v if isinstance(v, (int, float, str, bool, type(None))) else repr(v))
+          for k, v in sorted(keyargs.items()) if k not in ('device', 'verbose')}
+    return dict(n_cells=int(Nc), n_events=int(Ng), n_gene=int(n_gene), world=int(world),
+                Xc_sha1=hashlib.sha1(np.ascontiguousarray(Xc, dtype=np.float32).tobytes()).hexdigest(),
+                LRT_index=[int(i) for i in LRT_index], layer_keys=list(layer_keys),
+                intercept=None if intercept is None else float(intercept), intercept_mode=str(intercept_mode),
+                pseudo_count=float(pseudo_count), sigma=None if sigma is None else float(sigma),
+                base_mode=str(base_mode), fit=kw)
+
+
+def _balanced_chunk(n_events, budget, n_gene):
+    """Events per device chunk: whole convergence groups, at most `budget` events, and chunks of
+    (nearly) equal size -- 10 000 events under a budget of 9 580 run as 2 x 5 000, not 9 580 + 420
+    (a sliver of a chunk pays the full step count at a fraction of the bandwidth)."""
+    budget = max(budget // n_gene, 1) * n_gene
+    n_chunks = max(-(-n_events // budget), 1)
+    groups = -(-n_events // n_gene)
+    return max(-(-groups // n_chunks), 1) * n_gene
+
+
 def _device_event_budget(Nc, n_models, n_layers, device=None, frac=0.7):
     """Events per device chunk so that counts + (1+T) model states + outputs fit in HBM."""
     import torch
@@ -345,6 +378,9 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
     `out_dir` (not in the reference): directory for `.npy` memory maps of the dense
     (cells, events) outputs Psi / Psi95CI / Z_std / Z_loc, written event chunk by event chunk
     (and rank by rank) -- for fits whose outputs exceed host RAM; default: RAM arrays.
+    `resume` (not in the reference; needs `out_dir`): every finished event chunk is checkpointed
+    under `out_dir`; with resume=True a re-run of the same fit (same data shape, design, seed and
+    schedule) skips the chunks already there and returns what the uninterrupted fit would have.
 
     Returns the BRIE_RV result and adds to `adata` exactly the keys the reference adds
     (obsm['Xc'], varm['cell_coeff'], varm['Xg'], obsm['gene_coeff'], varm|obsm['intercept',
@@ -360,6 +396,7 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
     Nc, Ng = adata.shape
     n_models = 1 + len(LRT_index)
     out_dir = keyargs.pop('out_dir', None)
+    resume = keyargs.pop('resume', False)
 
     dist, rank, world = _dist_info()
     if (Xg is None or Xg.shape[1] == 0) and intercept_mode.upper() != 'CELL':   # :241
@@ -367,14 +404,21 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
         # _n_gene events (:242-258).  We keep _n_gene as the convergence group, fit as many
         # groups per launch as HBM holds, and give each GPU a contiguous range of groups.
         _n_gene = int(np.ceil(batch_size / Nc))
-        chunk = _device_event_budget(Nc, n_models, len(layer_keys), keyargs.get('device'))
-        chunk = max(chunk // _n_gene, 1) * _n_gene
         lo, hi = event_shards(Ng, world, _n_gene)[rank]
+        chunk = _device_event_budget(Nc, n_models, len(layer_keys), keyargs.get('device'))
+        chunk = _balanced_chunk(hi - lo, chunk, _n_gene)
         # finished chunks go straight into their column range of the output arrays (RAM, or
         # .npy memory maps under out_dir shared by all ranks) instead of np.append (:55-76)
-        store = LayerStore(Nc, Ng, out_dir, rank, world, dist)
+        signature = _fit_signature(Nc, Ng, Xc, LRT_index, layer_keys, _n_gene, world, intercept, intercept_mode,
+                                   pseudo_count, sigma, base_mode, keyargs) if out_dir is not None else None
+        store = LayerStore(Nc, Ng, out_dir, rank, world, dist, signature=signature, resume=resume)
         res_list = []
         for e0 in range(lo, hi, chunk):
+            _done = store.load_chunk(e0, min(e0 + chunk, hi))
+            if _done is not None:
+                res_list.append(_done)
+                print("[BRIE2] %d out %d genes done (resumed from %s)" % (min(e0 + chunk, hi) - lo, hi - lo, out_dir))
+                continue
             _idx = slice(e0, min(e0 + chunk, hi))
             _count_layers = [adata.layers[_key][:, _idx] for _key in layer_keys]
             _effLen = adata.varm['effLen'][_idx, :] if 'effLen' in adata.varm else None
@@ -384,7 +428,10 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
                 LRT_index=LRT_index, pseudo_count=pseudo_count, sigma=sigma,
                 base_mode=base_mode, tau_prior=tau_prior, group_size=_n_gene,
                 event_offset=e0, n_events_total=Ng, **keyargs)
+            _t0 = time.perf_counter()
             store.put(e0, _ResVal)
+            if getattr(_ResVal, 'timing', None) is not None:
+                _ResVal.timing['store.put'] = time.perf_counter() - _t0
             res_list.append(_ResVal)
             print("[BRIE2] %d out %d genes done" % (min(e0 + chunk, hi) - lo, hi - lo))
         if world > 1:                      # per-event vectors: every rank gets all of them, in event order

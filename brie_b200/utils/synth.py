@@ -76,16 +76,19 @@ def simulate_counts(Nc, Ng, design='none', seed=0, with_efflen=True, n_layers=3,
 
 
 def simulate_counts_device(Nc, Ng, design='none', seed=0, with_efflen=True, n_layers=3, effect_frac=0.1,
-                           pseudo_count=0.01, event_offset=0, device="cuda"):
+                           pseudo_count=0.01, event_offset=0, device="cuda", Xc=None):
     """Same recipe as simulate_counts, drawn on the GPU (brie_simulate_counts): the per-event
-    parameters come from numpy (small), the (cells, events) counts never touch host RAM.
+    parameters come from numpy (small), the (cells, events) counts never touch host RAM.  `Xc` overrides the design drawn from `seed`.
     Returns dict(layers=[device tensors (Nc, ld) with the pseudo-count applied], ld, effLen, Xc, truth)."""
     import ctypes as C
     import torch
     from .. import _lib
     lib = _lib.load()
     rng = np.random.default_rng(seed)
-    Xc = make_design(Nc, design, rng)
+    if Xc is None:
+        Xc = make_design(Nc, design, rng)
+    else:                                  # a design shared by several event blocks (seed = block)
+        Xc = np.asarray(Xc, np.float32)
     Kc = Xc.shape[1]
     ld = (Ng + 31) // 32 * 32
     pad = lambda v, fill=0.0: np.concatenate([v, np.full(ld - Ng, fill)]).astype(np.float32)

@@ -232,6 +232,51 @@ def test_fitBRIE_chunked_memmap_outputs_equal_single_chunk(tmp_path, monkeypatch
     assert np.array_equal(np.asarray(ad1.layers['Psi_95CI']), np.asarray(ad2.layers['Psi_95CI']))
 
 
+def test_fitBRIE_resume_from_checkpointed_chunks(tmp_path, monkeypatch):
+    """A fit that dies after two of three event chunks and is re-run with resume=True refits only the
+    last chunk and returns exactly what the uninterrupted fit returns."""
+    import brie_b200.models.model_wrap as mw
+    from brie_b200.models import fitBRIE
+    from brie_b200.utils.anndata_lite import AnnDataLite
+    Nc, Ng = 100, 90
+    data, effLen, Xc, _ = make_lrt_problem(Nc, Ng, seed=7)
+    kw = dict(Xc=Xc, LRT_index=None, intercept_mode='gene', batch_size=100 * 20, seed=4, min_iter=300, max_iter=800,
+              MC_size=2, n_eval=10)
+    monkeypatch.setattr(mw, "_device_event_budget", lambda *a, **k: 45)        # chunks of 40, 40, 10 events
+
+    def adata():
+        return AnnDataLite(X=data[0] + data[1] + data[2],
+                           layers={'isoform1': data[0].copy(), 'isoform2': data[1].copy(), 'ambiguous': data[2].copy()},
+                           varm={'effLen': effLen})
+
+    ref = fitBRIE(adata(), out_dir=str(tmp_path / "a"), **kw)
+    real_fit, calls = mw.fit_BRIE_matrix, []
+
+    def dying_fit(*a, **k):
+        if len(calls) == 2:
+            raise KeyboardInterrupt("job killed")
+        calls.append(k['event_offset'])
+        return real_fit(*a, **k)
+
+    monkeypatch.setattr(mw, "fit_BRIE_matrix", dying_fit)
+    with pytest.raises(KeyboardInterrupt):
+        fitBRIE(adata(), out_dir=str(tmp_path / "b"), resume=True, **kw)
+    assert calls == [0, 40] and os.path.exists(str(tmp_path / "b" / "chunk_40_80.pkl"))
+    calls2 = []
+    monkeypatch.setattr(mw, "fit_BRIE_matrix", lambda *a, **k: (calls2.append(k['event_offset']), real_fit(*a, **k))[1])
+    ad = adata()
+    res = fitBRIE(ad, out_dir=str(tmp_path / "b"), resume=True, **kw)
+    assert calls2 == [80]                                                       # only the missing chunk was fitted
+    for k in ('Psi', 'Psi95CI', 'Z_std', 'Z_loc', 'loss_gene', 'ELBO_gain', 'pval', 'fdr', 'losses', 'cell_coeff',
+              'sigma', 'intercept', 'n_iter'):
+        assert np.array_equal(np.asarray(getattr(ref, k)), np.asarray(getattr(res, k))), k
+    assert np.array_equal(np.asarray(ad.layers['Psi']), np.asarray(ref.Psi))
+    # a different seed is a different fit: nothing is reused
+    calls2.clear()
+    fitBRIE(adata(), out_dir=str(tmp_path / "b"), resume=True, **dict(kw, seed=5))
+    assert calls2 == [0, 40, 80]
+
+
 def test_one_vs_rest_lrt_with_15_covariates_null_base():
     """The reference's dentate-gyrus run (brie-tutorials/dentateGyrus/run_brie2.sh:31-36): 15 cell
     covariates (detection rate + 14 cluster indicators), --testBase null, LRT on 1..14.  Each

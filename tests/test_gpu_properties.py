@@ -1,0 +1,153 @@
+"""Size-independent properties of the fused fit at BASELINE.json's C2 size (5 000 x 5 000 -- too
+large for the CPU oracle) and oracle parity on ragged / degenerate shapes.
+
+Properties used (all follow from the reference's model, model_TFProb.py:118-211):
+  * events are independent when the intercept is per event and Kg = 0 (every parameter is per
+    event, model_wrap.py:241-260 relies on the same fact) => fitting an event range alone, with the
+    global event offset in the noise counters, reproduces that range of the whole fit;
+  * LRT refits are independent models => batching them in one launch changes nothing;
+  * an element without reads has zero likelihood gradient => its Z_loc / Z_std_log
+    gradient is the closed-form KL gradient, whatever the noise;
+  * same seed => same result, bit for bit (no atomics anywhere on the path).
+"""
+import numpy as np
+import pytest
+
+from oracle import philox_np as px
+from oracle.brie2_oracle import OracleBRIE2, add_pseudo_count
+
+from util import device_eps_provider, make_problem
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _c2_problem():
+    from brie_b200.utils.synth import simulate_counts_device
+    return simulate_counts_device(5000, 5000, design='binary1', seed=2, with_efflen=True, n_layers=3)
+
+
+def _run(sim, cols=None, masks=([0], []), model_ids=None, steps=12, seed=5):
+    """12 steps (2 with the loss trace) of a fresh engine on all events or on the event range `cols`."""
+    from brie_b200.engine import FitEngine
+    lo, hi = (0, 5000) if cols is None else cols
+    layers = sim['layers'] if cols is None else [t[:, lo:hi] for t in sim['layers']]
+    eng = FitEngine(layers, effLen=sim['effLen'][lo:hi], Xc=sim['Xc'], masks=[list(m) for m in masks],
+                    model_ids=model_ids, MC_size=3, seed=seed, trace_cap=4, event_offset=lo,
+                    n_events_total=5000, n_events=hi - lo, group_size=100)
+    eng.init_params()
+    eng.begin_stage(0.01)
+    eng.run_steps(steps - 2)
+    eng.run_steps(2, 0)
+    torch.cuda.synchronize()
+    n = hi - lo
+    return dict(Z_loc=eng.Z_loc[:, :, :n].clone(), Z_std_log=eng.Z_std_log[:, :, :n].clone(),
+                Wc=eng.Wc[:, :, :n].clone(), b=eng.intercept[:, :n].clone(), tau=eng.sigma_log[:, :n].clone(),
+                trace=eng.loss_trace[:, :2, :n].clone(), rows_per_cta=eng.sizes.rows_per_cta)
+
+
+def _same(a, b, exact):
+    for k in ('Z_loc', 'Z_std_log', 'Wc', 'b', 'tau', 'trace'):
+        if exact:
+            assert torch.equal(a[k], b[k]), k
+        else:       # a different row chunking only reorders float32 partial sums of the per-event gradients
+            scale = max(float(a[k].abs().max()), 1.0)
+            assert float((a[k] - b[k]).abs().max()) <= 2e-5 * scale, k
+
+
+def test_c2_full_size_determinism_sharding_and_batching_invariance():
+    sim = _c2_problem()
+    whole = _run(sim)
+    assert torch.isfinite(whole['Z_loc']).all() and torch.isfinite(whole['trace']).all()
+    # 1. determinism, bit for bit
+    again = _run(sim)
+    _same(whole, again, exact=True)
+    # 2. event sharding: a group-aligned and a ragged (not a multiple of 32) cut
+    for lo, hi in [(0, 2500), (2500, 5000), (1217, 3001)]:
+        part = _run(sim, cols=(lo, hi))
+        ref = {k: (v[..., lo:hi] if k != 'rows_per_cta' else v) for k, v in whole.items()}
+        _same(ref, part, exact=part['rows_per_cta'] == whole['rows_per_cta'])
+    # 3. model batching: the full model and the refit fitted alone (same RNG model words)
+    for m, mask in enumerate(([0], [])):
+        alone = _run(sim, masks=(mask,), model_ids=[m])
+        kc = len(mask)
+        ref = {k: (v[m:m + 1] if k != 'rows_per_cta' else v) for k, v in whole.items()}
+        ref['Wc'], alone['Wc'] = ref['Wc'][:, :kc], alone['Wc'][:, :kc]
+        _same(ref, alone, exact=alone['rows_per_cta'] == whole['rows_per_cta'])
+    # a different seed does change the result
+    other = _run(sim, seed=6)
+    assert not torch.equal(other['Z_loc'], whole['Z_loc'])
+
+
+def test_c2_full_size_zero_count_elements_follow_the_closed_form_kl_gradient():
+    """One step from a known state: for every element without reads the Adam first moments are
+    0.1 x the KL gradient  d/dZ_loc = (mu - m) / sigma^2,  d/dZ_std_log = s^2 / sigma^2 - 1."""
+    from brie_b200.engine import FitEngine
+    sim = _c2_problem()
+    eng = FitEngine(sim['layers'], effLen=sim['effLen'], Xc=sim['Xc'], masks=[[0]], MC_size=3, seed=9,
+                    trace_cap=2, n_events=5000)
+    eng.init_params()
+    Ng = 5000
+    mu, lam = eng.Z_loc[0, :, :Ng].double(), eng.Z_std_log[0, :, :Ng].double()
+    Xc = torch.from_numpy(sim['Xc']).to(mu.device).double()
+    prior = Xc @ eng.Wc[0, :1, :Ng].double() + eng.intercept[0, :Ng].double()[None, :]
+    tau = eng.sigma_log[0, :Ng].double()[None, :]
+    g_mu = (mu - prior) * torch.exp(-2 * tau)
+    g_lam = torch.exp(2 * (lam - tau)) - 1
+    zero = (sim['layers'][0][:, :Ng] + sim['layers'][1][:, :Ng] + sim['layers'][2][:, :Ng]) == 0
+    assert 0.7 < float(zero.float().mean()) < 0.95
+    eng.begin_stage(0.001)
+    eng.run_steps(1)
+    torch.cuda.synchronize()
+    m_mu, m_lam = 10 * eng.adam_Z[0, 0, :, :Ng].double(), 10 * eng.adam_Z[2, 0, :, :Ng].double()
+    assert float(((m_mu - g_mu)[zero]).abs().max()) <= 1e-5 * float(g_mu[zero].abs().max())
+    rel = ((m_lam - g_lam)[zero]).abs() / (1 + g_lam[zero].abs())
+    assert float(rel.max()) <= 1e-5
+    # elements with reads do get a likelihood term
+    assert float(((m_mu - g_mu)[~zero]).abs().max()) > 1e-2
+
+
+EDGE_SHAPES = [(1, 1), (1, 37), (5, 1), (3, 31), (9, 128), (257, 129), (300, 64)]
+
+
+@pytest.mark.parametrize("Nc,Ng", EDGE_SHAPES)
+@pytest.mark.parametrize("mode,Kc,Kg", [('gene', 1, 0), ('cell', 0, 2)])
+def test_ragged_and_degenerate_shapes_match_oracle(Nc, Ng, mode, Kc, Kg):
+    """Single cells / single events / tiles that end inside a lane vector, a row chunk or a warp,
+    an event without any read and a cell without any read: per-event loss and the per-element
+    gradients of the first step against the float64 oracle."""
+    from brie_b200.engine import FitEngine
+    S, seed = 3, 21
+    data, effLen, Xc, Xg = make_problem(Nc, Ng, Kc, Kg, True, 3, seed=4)
+    for d in data:
+        d[:, Ng // 2] = 0                    # an event nobody covers
+        d[Nc // 2, :] = 0                    # a cell without reads
+    if Nc > 1 and Ng > 1:
+        data[0][0, 0] = 7                    # make sure something is non-zero
+    add_pseudo_count(data, np.float32(0.01))
+    eng = FitEngine(data, effLen=effLen, Xc=Xc, Xg=Xg, intercept_mode=mode, MC_size=S, seed=seed, trace_cap=4)
+    eng.init_params()
+    om = OracleBRIE2(Nc, Ng, Kc, Kg, effLen, None, mode, None, dtype=np.float64, seed=seed)
+    pr = eng.model_params(0)
+    om.p['Z_loc'] = eng.Z_loc[0, :, :Ng].cpu().numpy().astype(np.float64)
+    om.p['Z_std_log'] = eng.Z_std_log[0, :, :Ng].cpu().numpy().astype(np.float64)
+    om.p['Wc_loc'] = pr['Wc_loc'].astype(np.float64)
+    om.p['Wg_loc'] = pr['Wg_loc'].astype(np.float64)
+    om.p['intercept'] = pr['intercept'].astype(np.float64)
+    om.Xc, om.Xg = Xc.astype(np.float64), Xg.astype(np.float64)
+    eps = device_eps_provider(seed, 0, Nc, Ng)(px.PHASE_TRAIN, 0, S)
+    loss, loss_gene, grads = om.loss_and_grads(data, eps)
+    eng.begin_stage(0.001)
+    eng.run_steps(1, 0)
+    torch.cuda.synchronize()
+    tr = eng.loss_trace[0, 0, :Ng].cpu().numpy()
+    assert np.all(np.isfinite(tr))
+    assert np.abs(tr - loss_gene).max() <= 1e-4 * max(np.abs(loss_gene).max(), 1.0)
+    for slot, name in ((0, 'Z_loc'), (2, 'Z_std_log')):
+        dev = 10 * eng.adam_Z[slot, 0, :, :Ng].cpu().numpy()
+        assert np.abs(dev - grads[name]).max() <= 2e-4 * max(np.abs(grads[name]).max(), 1.0), name
+    lg = eng.eval_loss_gene(3)
+    assert torch.isfinite(lg).all()
+    Psi, CI, Zs = eng.posterior(0)
+    assert Psi.shape == (Nc, Ng) and float(Psi.min()) >= 0 and float(Psi.max()) <= 1 and float(CI.min()) >= 0

@@ -185,6 +185,47 @@ def test_layer_store_ram_and_memmap(tmp_path):
             assert np.array_equal(np.load(os.path.join(out_dir, "Psi.npy")), full['Psi'])
 
 
+def test_layer_store_checkpoint_and_resume(tmp_path):
+    """Finished chunks leave a checkpoint; a resumed store with the same signature hands them back
+    and keeps the big arrays, a different signature (or resume=False) starts from scratch."""
+    from brie_b200.utils.layer_store import LayerStore, BIG_KEYS
+    from brie_b200.models.model_wrap import BRIE_RV
+    rng = np.random.default_rng(1)
+    Nc, Ng = 7, 30
+    full = {k: rng.standard_normal((Nc, Ng)).astype(np.float32) for k in BIG_KEYS}
+    out_dir = str(tmp_path / "ckpt")
+    sig = dict(n_cells=Nc, n_events=Ng, fit=dict(seed=3, min_iter=600), LRT_index=[0])
+
+    def chunk(e0, e1):
+        rv = BRIE_RV()
+        rv.Nc, rv.Ng = Nc, e1 - e0
+        rv.loss_gene = np.arange(e0, e1, dtype=np.float32)
+        for k in BIG_KEYS:
+            setattr(rv, k, full[k][:, e0:e1].copy())
+        return rv
+
+    st = LayerStore(Nc, Ng, out_dir, signature=sig, resume=True)      # nothing to resume yet
+    assert not st.resumed and st.load_chunk(0, 10) is None
+    st.put(0, chunk(0, 10))
+    st.put(10, chunk(10, 20))                                         # ... and the job dies here
+    del st
+    st = LayerStore(Nc, Ng, out_dir, signature=sig, resume=True)
+    assert st.resumed
+    done = [st.load_chunk(0, 10), st.load_chunk(10, 20)]
+    assert all(d is not None for d in done) and st.load_chunk(20, 30) is None
+    assert np.array_equal(done[1].loss_gene, np.arange(10, 20, dtype=np.float32)) and done[1].Psi.shape == (Nc, 0)
+    st.put(20, chunk(20, 30))
+    got = st.finish()
+    for k in BIG_KEYS:
+        assert np.array_equal(np.asarray(got[k]), full[k])
+    # another fit in the same directory does not pick these chunks up
+    st = LayerStore(Nc, Ng, out_dir, signature=dict(sig, fit=dict(seed=4, min_iter=600)), resume=True)
+    assert not st.resumed and st.load_chunk(0, 10) is None
+    assert not any(f.startswith("chunk_") for f in os.listdir(out_dir))
+    st = LayerStore(Nc, Ng, out_dir, signature=sig, resume=False)
+    assert not st.resumed
+
+
 def test_layer_store_two_process_gloo(tmp_path):
     """world_size 2 (gloo): both ranks write their event ranges; RAM mode exchanges blocks,
     memmap mode shares the files -- every rank ends with the full arrays."""
