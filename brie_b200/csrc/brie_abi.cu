@@ -50,6 +50,11 @@ struct brie_fit {
   // optional CUDA-event timing of the fused step kernel (bench.py roofline)
   std::vector<cudaEvent_t> ev0, ev1;
   int ev_used = 0;
+  // column compaction of the step kernel (brie_fit_set_active_blocks); null = all columns
+  const int32_t* blk_ids = nullptr;
+  int64_t blk_stride = 0;
+  int32_t n_blk[BRIE_MAX_MODELS] = {0};
+  int blk_tiles = 0;
 };
 
 using namespace brie;
@@ -378,7 +383,13 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
     a.model_mask = mmask;
     a.M = M; a.S = d.mc_size; a.rows_per_cta = f->sz.rows_per_cta;
     for (int m = 0; m < M; ++m) a.model_id[m] = d.model_id[m];
-    const dim3 grid(M, f->sz.n_col_tiles, f->sz.n_row_chunks);
+    dim3 grid(M, f->sz.n_col_tiles, f->sz.n_row_chunks);
+    if (f->blk_ids) {
+      a.blk_ids = f->blk_ids;
+      a.blk_stride = f->blk_stride;
+      for (int m = 0; m < M; ++m) a.n_blk[m] = f->n_blk[m];
+      grid.y = (unsigned)(f->blk_tiles > 0 ? f->blk_tiles : 1);
+    }
     const bool timed = f->ev_used < (int)f->ev0.size();
     if (timed) BRIE_CUDA(cudaEventRecord(f->ev0[f->ev_used], s));
     BRIE_CUDA(dispatch_step(a, d.Kc, d.Kg, d.cell_mode != 0, loss, grid, s));
@@ -456,6 +467,35 @@ int brie_fit_run_steps(brie_fit* f, int32_t n_steps, int32_t trace_slot0, void* 
     rc = brie_fit_step_phase(f, 1, slot, stream);
     if (rc) return rc;
   }
+  return BRIE_OK;
+}
+
+int brie_fit_set_active_blocks(brie_fit* f, const int32_t* blk_ids, int64_t blk_stride, const int32_t* n_blk_host) {
+  if (!f || !f->bound) return fail(BRIE_ERR_ARG, "fit not bound");
+  if (f->step_open) return fail(BRIE_ERR_ARG, "a split step is still open");
+  if (!blk_ids) {
+    f->blk_ids = nullptr;
+    f->blk_stride = 0;
+    f->blk_tiles = 0;
+    return BRIE_OK;
+  }
+  const brie_fit_desc& d = f->d;
+  if (f->ncell > 0 || d.target != BRIE_TARGET_ELBO)
+    return fail(BRIE_ERR_UNSUPPORTED, "column compaction needs per-event parameters only (Kg = 0, gene intercept) and target ELBO");
+  if (d.ld % 8 != 0) return fail(BRIE_ERR_ARG, "column compaction needs ld %% 8 == 0");
+  if (!n_blk_host || blk_stride < 1) return fail(BRIE_ERR_ARG, "n_blk_host and blk_stride required");
+  const int bpt = step_tile_cols(d.Kc) / kBlkCols;
+  int tiles = 0;
+  for (int m = 0; m < d.n_models; ++m) {
+    if (n_blk_host[m] < 0 || n_blk_host[m] > blk_stride || (int64_t)n_blk_host[m] * kBlkCols > d.ld)
+      return fail(BRIE_ERR_ARG, "n_blk_host[%d] = %d out of range", m, n_blk_host[m]);
+    f->n_blk[m] = n_blk_host[m];
+    const int t = (int)ceil_div(n_blk_host[m], bpt);
+    if (t > tiles) tiles = t;
+  }
+  f->blk_ids = blk_ids;
+  f->blk_stride = blk_stride;
+  f->blk_tiles = tiles;
   return BRIE_OK;
 }
 

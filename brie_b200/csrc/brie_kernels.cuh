@@ -61,7 +61,15 @@ struct StepArgs {
   uint32_t model_mask;  // bit m: model m has any active event
   int32_t M, S, rows_per_cta;
   int32_t model_id[kMaxModels];
+  // Optional column compaction (extension rounds, when most reference batches have converged):
+  // model m visits only the 8-event blocks blk_ids[m * blk_stride + 0 .. n_blk[m]) -- the blocks that
+  // still hold an active event -- packed 4 * EPL to a tile.  Null = every column, in order.
+  const int32_t* blk_ids;
+  int64_t blk_stride;
+  int32_t n_blk[kMaxModels];
 };
+
+constexpr int kBlkCols = 8;   // events per compaction block = one 32-byte sector of every f32 array
 
 __device__ __forceinline__ float sqrt_approx(float x) {
   float y;
@@ -227,14 +235,19 @@ __host__ __device__ constexpr int step_tile_cols(int KC) { return 32 * step_epl(
 // they are not live across the Monte-Carlo phase (no spills).  Measured on one box (profiles/
 // r1_ab_smem_consts.md): C3 with loss trace +11 %, C4 +10 % / +23 %, Kc 15 +9 %; only Kc <= 4 without
 // gene features and without the loss trace is faster from registers (C3: 4 %).
+#ifndef BRIE_SMEM_CONSTS_MODE
+#define BRIE_SMEM_CONSTS_MODE 0   // A/B aid (scripts/ab.sh): 1 = shared memory whenever Kc + Kg >= 3, 2 = never
+#endif
 __host__ __device__ constexpr bool step_consts_in_smem(int KC, int KG, bool LOSS) {
+  if (BRIE_SMEM_CONSTS_MODE == 1) return KC + KG >= 3;
+  if (BRIE_SMEM_CONSTS_MODE == 2) return false;
   return KC + KG >= 3 && !(KG == 0 && KC <= 4 && !LOSS);
 }
 __host__ __device__ constexpr int step_n_consts(int KC, int KG, bool CELL, bool LOSS) {
   return step_consts_in_smem(KC, KG, LOSS) ? KC + KG + (CELL ? 0 : 3) : 0;
 }
 __host__ __device__ constexpr int step_smem_bytes(int KC, int KG, bool CELL, bool LOSS) {
-  return (kWarps * kRingStages * kRingArrays + kWarps * kQueueFields + 6 + step_n_consts(KC, KG, CELL, LOSS)) *
+  return (kWarps * kRingStages * kRingArrays + kWarps * kQueueFields + 7 + step_n_consts(KC, KG, CELL, LOSS)) *
          step_tile_cols(KC) * 4;
 }
 
@@ -252,7 +265,24 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   const int tile = blockIdx.y;
   const int chunk = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t g0 = (int64_t)tile * TC + lane * EPL;
+  // column of this lane's first event, and of tile column threadIdx.x (per-event constants, partial sums)
+  constexpr int LPB = kBlkCols / EPL;       // lanes per compaction block
+  constexpr int BPT = TC / kBlkCols;        // blocks per tile
+  int64_t g0 = (int64_t)tile * TC + lane * EPL;
+  if (a.blk_ids != nullptr) {
+    const int nblk = a.n_blk[m];
+    if (tile * BPT >= nblk) return;
+    const int bl = tile * BPT + lane / LPB;
+    g0 = bl < nblk ? (int64_t)a.blk_ids[(int64_t)m * a.blk_stride + bl] * kBlkCols + (lane % LPB) * EPL : a.ld;
+  }
+  // recomputed where needed (constants load, final partial sums) rather than kept live across the row loop
+  auto thread_col = [&]() -> int64_t {
+    if (a.blk_ids == nullptr) return (int64_t)tile * TC + threadIdx.x;
+    const int bt = tile * BPT + (int)(threadIdx.x / kBlkCols);
+    return (threadIdx.x < TC && bt < a.n_blk[m])
+               ? (int64_t)a.blk_ids[(int64_t)m * a.blk_stride + bt] * kBlkCols + (threadIdx.x % kBlkCols)
+               : a.ld;
+  };
   const bool in_ld = g0 < a.ld;             // ld % 4 == 0 and EPL divides 4: a lane is all in or all out
 
   uint32_t act = 0;                         // bit j: this lane's event j is still being optimised
@@ -269,7 +299,8 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
                                                  warp * kQueueFields * TC);
   float(*s_L)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * kRingArrays * TC +
                                                    kWarps * kQueueFields * TC);
-  float(*s_k)[TC] = s_L + 6;                // kSm: rows Wc[0..KC), Xg[0..KG), then (gene mode) b, tau, 1/sigma^2
+  uint32_t* s_ev = reinterpret_cast<uint32_t*>(s_L + 6);   // global event id of each tile column (RNG counter word)
+  float(*s_k)[TC] = s_L + 7;                // kSm: rows Wc[0..KC), Xg[0..KG), then (gene mode) b, tau, 1/sigma^2
 
   const int64_t row_begin = (int64_t)chunk * a.rows_per_cta;
   const int64_t row_end = min(row_begin + (int64_t)a.rows_per_cta, a.Nc);
@@ -302,7 +333,8 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 
   // per-event constants
   if (threadIdx.x < TC) {
-    const int64_t g = (int64_t)tile * TC + threadIdx.x;
+    const int64_t g = thread_col();
+    s_ev[threadIdx.x] = (uint32_t)(a.event_offset + g);
     float l1 = 1.f, l2 = 1.f, l3 = 0.f;
     if (a.eff && g < a.ld) { l1 = a.eff[g]; l2 = a.eff[a.ld + g]; l3 = a.eff[2 * a.ld + g]; }
     s_L[0][threadIdx.x] = l1; s_L[1][threadIdx.x] = l2; s_L[2][threadIdx.x] = l3;
@@ -364,7 +396,6 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     for (int j = 0; j < EPL; ++j) acc[i][j] = 0.f;
 
   const uint32_t stream0 = brie_stream_word(BRIE_PHASE_TRAIN, (uint32_t)a.model_id[m], 0u);
-  const uint32_t ev0 = (uint32_t)(a.event_offset + (int64_t)tile * TC);
   const uint32_t lt_mask = (1u << lane) - 1u;
 
   // per-row (cell) constants are warp-uniform loads; fetch them one row ahead so their latency
@@ -492,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
         const int col = __float_as_int(q[5][k]);
         const float l1 = s_L[0][col], l2 = s_L[1][col], l3 = s_L[2][col];
         float gs, ge, ls;
-        mc_samples<LOSS>(imu, is, ic1, ic2, in, l1, l2, l3, l1 - l2, a.S, ev0 + (uint32_t)col, (uint32_t)row,
+        mc_samples<LOSS>(imu, is, ic1, ic2, in, l1, l2, l3, l1 - l2, a.S, s_ev[col], (uint32_t)row,
                          a.step, stream0, a.seed, gs, ge, ls);
         q[2][k] = gs * a.inv_S;
         q[3][k] = ge * is * a.inv_S;
@@ -558,7 +589,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   if (NEV > 0) {
     __syncthreads();  // all warps are done with their queues; reuse the memory for the reduction
     float(*red)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * kRingArrays * TC);
-    const int64_t gcol = (int64_t)tile * TC + threadIdx.x;
+    const int64_t gcol = thread_col();
 #pragma unroll
     for (int i = 0; i < NEV; ++i) {
       *reinterpret_cast<Vec*>(&red[warp][lane * EPL]) = vec_make<EPL>(acc[i]);

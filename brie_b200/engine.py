@@ -10,6 +10,7 @@ torch is used for device memory, streams and (optionally) torch.distributed --
 all arithmetic on the path happens in libbrie_b200.so.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -264,11 +265,29 @@ class FitEngine:
         return out.cpu().numpy()
 
     def set_active_groups(self, act):
-        """act: (M, n_groups) bool -> per-event active mask."""
+        """act: (M, n_groups) bool -> per-event active mask.  When some reference batches are
+        frozen the step kernel is pointed at the 8-event column blocks that still hold an active
+        event (brie_fit_set_active_blocks): an extension round then costs what its active events
+        cost, not what the whole shard costs.  Bit-identical to the dense walk."""
         g = (np.arange(self.Ng) + self.event_offset) // self.group_size - self.first_group
         ev = np.zeros((self.M, self.ld), np.uint8)
         ev[:, :self.Ng] = act[:, g]
         self.active.copy_(torch.from_numpy(ev).to(self.device))
+        if self.shared or self.target != "ELBO" or os.environ.get("BRIE_NO_COMPACT"):
+            return
+        blk = ev.reshape(self.M, self.ld // 8, 8).any(axis=2)
+        if blk[:, :(self.Ng + 7) // 8].all():
+            self._blk_ids = None
+            _lib.check(self.lib.brie_fit_set_active_blocks(self.h, None, 0, None))
+            return
+        n_blk = blk.sum(axis=1).astype(np.int32)
+        stride = max(int(n_blk.max()), 1)
+        ids = np.zeros((self.M, stride), np.int32)
+        for m in range(self.M):
+            ids[m, :n_blk[m]] = np.flatnonzero(blk[m])
+        self._blk_ids = torch.from_numpy(ids).to(self.device)       # kept alive while the handle points at it
+        _lib.check(self.lib.brie_fit_set_active_blocks(
+            self.h, self._blk_ids.data_ptr(), stride, n_blk.ctypes.data_as(C.POINTER(C.c_int32))))
 
     def eval_loss_gene(self, n_eval=500, mc_size=1):
         """Mean of n_eval per-event loss evaluations (model_TFProb.py:261-264); each evaluation

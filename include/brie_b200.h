@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define BRIE_ABI_VERSION 2
+#define BRIE_ABI_VERSION 3
 #define BRIE_MAX_MODELS 32
 #define BRIE_MAX_KC 16
 #define BRIE_MAX_KG 8
@@ -125,6 +125,18 @@ int brie_fit_begin_stage(brie_fit* fit, float lr, void* stream);
  * If trace_slot0 >= 0 the pre-update per-event loss of step i is written to
  * loss_trace[:, trace_slot0 + i, :]; if < 0 the loss is not evaluated. */
 int brie_fit_run_steps(brie_fit* fit, int32_t n_steps, int32_t trace_slot0, void* stream);
+
+/* Column compaction for the convergence-extension rounds (model_TFProb.py:250-258).  The
+ * reference extends each event batch on its own (model_wrap.py:241-260); batches that have
+ * converged stay frozen through `active`.  Once most are frozen the step kernel can visit only
+ * the 8-event column blocks (one 32-byte sector of every f32 array) that still hold an active
+ * event: blk_ids (DEVICE, (n_models, blk_stride) int32, ascending block indices col / 8) lists
+ * them per model, n_blk_host (HOST, n_models) their counts.  Results are bit-identical to the
+ * uncompacted step.  blk_ids = NULL restores the dense walk.  The list must cover every event
+ * with active = 1 and must stay valid until replaced.  Needs ld % 8 == 0, Kg = 0, cell_mode = 0,
+ * target ELBO. */
+int brie_fit_set_active_blocks(brie_fit* fit, const int32_t* blk_ids, int64_t blk_stride,
+                               const int32_t* n_blk_host);
 
 /* All-reduce hook for event-sharded fits with shared per-cell parameters
  * (Kg > 0 or cell_mode).  brie_fit_run_steps_split runs ONE step in two halves:
