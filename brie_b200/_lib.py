@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 BRIE_MAX_MODELS = 32
-ABI_VERSION = 3
+ABI_VERSION = 4
 TARGETS = {"ELBO": 0, "marginLik": 1}
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BRIE_LIB_PATH", os.path.join(_HERE, "libbrie_b200.so"))
@@ -22,7 +22,7 @@ class FitDesc(C.Structure):
         ("mc_size", C.c_int32), ("n_layers", C.c_int32), ("has_efflen", C.c_int32),
         ("cell_mode", C.c_int32), ("train_intercept", C.c_int32),
         ("train_sigma", C.c_int32), ("trace_cap", C.c_int32),
-        ("target", C.c_int32), ("reserved0", C.c_int32),
+        ("target", C.c_int32), ("rows_per_cta", C.c_int32),
         ("model_id", C.c_int32 * BRIE_MAX_MODELS),
         ("xc_mask", C.c_uint32 * BRIE_MAX_MODELS),
     ]
@@ -43,6 +43,7 @@ class FitBuffers(C.Structure):
         ("adam_Z", C.c_void_p), ("Wc", C.c_void_p), ("intercept", C.c_void_p),
         ("sigma_log", C.c_void_p), ("Wg", C.c_void_p), ("adam_small", C.c_void_p),
         ("active", C.c_void_p), ("loss_trace", C.c_void_p), ("scratch", C.c_void_p),
+        ("event_ids", C.c_void_p), ("counts_model_stride", C.c_int64), ("efflen_model_stride", C.c_int64),
     ]
 
 
@@ -57,6 +58,8 @@ SYMBOLS = {
     "brie_fit_bind": (C.c_int, [_P, C.POINTER(FitBuffers)]),
     "brie_fit_init_params": (C.c_int, [_P, C.c_float, C.c_float, _P]),
     "brie_fit_begin_stage": (C.c_int, [_P, C.c_float, _P]),
+    "brie_fit_resume_stage": (C.c_int, [_P, C.c_float, C.c_int64, C.c_uint32]),
+    "brie_fit_get_step": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]),
     "brie_fit_run_steps": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "brie_fit_set_active_blocks": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int32)]),
     "brie_fit_step_phase": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
@@ -79,6 +82,7 @@ SYMBOLS = {
     "brie_gene_stats_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int64]),
     "brie_gene_stats": (C.c_int, [C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "brie_gather_events": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_int64, C.c_int64, _P, _P]),
+    "brie_scatter_events": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_int64, C.c_int64, _P, _P]),
 }
 
 _lib = None

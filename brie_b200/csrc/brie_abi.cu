@@ -138,6 +138,7 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
   if (d.mc_size < 1 || d.mc_size > 4096) return fail(BRIE_ERR_ARG, "mc_size out of range");
   if (d.n_layers != 2 && d.n_layers != 3) return fail(BRIE_ERR_ARG, "n_layers must be 2 or 3");
   if (d.trace_cap < 0) return fail(BRIE_ERR_ARG, "trace_cap must be >= 0");
+  if (d.rows_per_cta < 0 || d.rows_per_cta > 65536) return fail(BRIE_ERR_ARG, "rows_per_cta out of range");
   if (d.target != BRIE_TARGET_ELBO && d.target != BRIE_TARGET_MARGINLIK)
     return fail(BRIE_ERR_ARG, "target must be BRIE_TARGET_ELBO or BRIE_TARGET_MARGINLIK");
   for (int m = 0; m < d.n_models; ++m) {
@@ -153,7 +154,9 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
   // >= ~10 waves of 2 CTAs/SM (tail effect); small problems go down to one row per warp
   int rows = 256;
   const char* env = getenv("BRIE_ROWS_PER_CTA");
-  if (env && atoi(env) > 0) {
+  if (d.rows_per_cta > 0) {
+    rows = d.rows_per_cta;
+  } else if (env && atoi(env) > 0) {
     rows = atoi(env);
   } else {
     const int64_t target = 148 * 2 * 10;
@@ -247,6 +250,12 @@ int brie_fit_bind(brie_fit* fit, const brie_fit_buffers* b) {
                            b->adam_Z,    b->Wc,        b->intercept, b->sigma_log, b->active, b->scratch};
   for (const void* p : aligned)
     if (((uintptr_t)p & 15u) != 0) return fail(BRIE_ERR_ARG, "device buffers must be 16-byte aligned");
+  if (b->event_ids || b->counts_model_stride != 0 || b->efflen_model_stride != 0) {
+    if (fit->ncell > 0 || d.target != BRIE_TARGET_ELBO)
+      return fail(BRIE_ERR_UNSUPPORTED, "a gathered sub-fit needs per-event parameters only (Kg = 0, gene intercept) and target ELBO");
+    if (b->counts_model_stride < 0 || b->counts_model_stride % 4 != 0 || b->efflen_model_stride < 0)
+      return fail(BRIE_ERR_ARG, "model strides must be >= 0 (counts: a multiple of 4 floats)");
+  }
   fit->buf = *b;
   fit->bound = true;
   return BRIE_OK;
@@ -320,6 +329,24 @@ int brie_fit_begin_stage(brie_fit* f, float lr, void* stream) {
   return BRIE_OK;
 }
 
+int brie_fit_resume_stage(brie_fit* f, float lr, int64_t adam_t, uint32_t global_step) {
+  if (!f || !f->bound) return fail(BRIE_ERR_ARG, "fit not bound");
+  if (f->step_open) return fail(BRIE_ERR_ARG, "a split step is still open");
+  if (adam_t < 0) return fail(BRIE_ERR_ARG, "adam_t must be >= 0");
+  f->stage_open = true;
+  f->lr = lr;
+  f->t = adam_t;
+  f->global_step = global_step;
+  return BRIE_OK;
+}
+
+int brie_fit_get_step(const brie_fit* f, int64_t* adam_t, uint32_t* global_step) {
+  if (!f || !adam_t || !global_step) return fail(BRIE_ERR_ARG, "null argument");
+  *adam_t = f->t;
+  *global_step = f->global_step;
+  return BRIE_OK;
+}
+
 int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* stream) {
   if (!f || !f->bound) return fail(BRIE_ERR_ARG, "fit not bound");
   cudaStream_t s = (cudaStream_t)stream;
@@ -338,6 +365,7 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
     const bool margin = d.target == BRIE_TARGET_MARGINLIK;
     int nev = d.Kc + (d.cell_mode ? 0 : 2) + (loss ? 1 : 0);
     int cell_tiles = f->sz.n_col_tiles;
+    if (margin && f->buf.event_ids) return fail(BRIE_ERR_UNSUPPORTED, "marginLik on a gathered sub-fit");
     if (margin) {
       // prior-sampled objective: counts only, no per-element state (brie_margin.cuh)
       nev = d.Kc + (d.cell_mode ? 0 : 2) + 1;
@@ -383,6 +411,9 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
     a.model_mask = mmask;
     a.M = M; a.S = d.mc_size; a.rows_per_cta = f->sz.rows_per_cta;
     for (int m = 0; m < M; ++m) a.model_id[m] = d.model_id[m];
+    a.ev_ids = f->buf.event_ids;
+    a.c_mstride = f->buf.counts_model_stride;
+    a.eff_mstride = f->buf.efflen_model_stride;
     dim3 grid(M, f->sz.n_col_tiles, f->sz.n_row_chunks);
     if (f->blk_ids) {
       a.blk_ids = f->blk_ids;
@@ -509,6 +540,8 @@ int brie_fit_cell_grad(brie_fit* f, float** ptr, int64_t* n_floats) {
 int brie_fit_eval_loss_gene(brie_fit* f, int32_t n_eval, int32_t mc_size, float* loss_gene, void* stream) {
   if (!f || !f->bound || !loss_gene) return fail(BRIE_ERR_ARG, "null argument or fit not bound");
   if (n_eval < 1) return fail(BRIE_ERR_ARG, "n_eval must be >= 1");
+  if (f->buf.event_ids || f->buf.counts_model_stride || f->buf.efflen_model_stride)
+    return fail(BRIE_ERR_UNSUPPORTED, "loss_gene is evaluated on the parent fit, not on a gathered sub-fit");
   if (mc_size < 1 || mc_size > 4096) return fail(BRIE_ERR_ARG, "mc_size out of range");
   cudaStream_t s = (cudaStream_t)stream;
   const brie_fit_desc& d = f->d;
@@ -552,6 +585,7 @@ int brie_fit_group_trace(brie_fit* f, int32_t n_slots, int64_t group_size, int64
   const brie_fit_desc& d = f->d;
   if (n_slots < 1 || n_slots > d.trace_cap) return fail(BRIE_ERR_ARG, "n_slots out of range");
   if (group_size < 1 || n_groups < 1) return fail(BRIE_ERR_ARG, "bad group geometry");
+  if (f->buf.event_ids) return fail(BRIE_ERR_UNSUPPORTED, "scatter the trace of a gathered sub-fit back to its parent first");
   const int64_t first_group = d.event_offset / group_size;
   const dim3 grid(n_slots, d.n_models);
   group_trace_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(f->buf.loss_trace, d.trace_cap, d.ld, d.n_events,

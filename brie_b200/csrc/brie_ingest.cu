@@ -110,6 +110,17 @@ __global__ void __launch_bounds__(256) gather_columns_kernel(const float* __rest
   }
 }
 
+// inverse of the gather: out[r, dst[j]] = in[r, j]; columns not listed keep their contents
+__global__ void __launch_bounds__(256) scatter_columns_kernel(const float* __restrict__ in, int64_t ld_in,
+                                                              const int64_t* __restrict__ dst, int64_t n_cells,
+                                                              int64_t n_in, int64_t ld_out, float* out) {
+  const int64_t total = n_cells * n_in;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / n_in, j = i % n_in;
+    out[r * ld_out + dst[j]] = in[r * ld_in + j];
+  }
+}
+
 namespace {
 int stats_chunks(int64_t n_cells, int64_t ld, int64_t* rows_per_chunk) {
   const int64_t tiles = ceil_div(ld, 128);
@@ -194,6 +205,17 @@ int brie_gather_events(int64_t n_cells, int64_t ld_in, const float* in, const in
   if (!in || !out || (n_out > 0 && !src)) return fail(BRIE_ERR_ARG, "null argument");
   gather_columns_kernel<<<grid_1d(n_cells * ld_out, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, src, n_cells,
                                                                                          n_out, ld_out, out);
+  BRIE_CUDA(cudaGetLastError());
+  return BRIE_OK;
+}
+
+int brie_scatter_events(int64_t n_cells, int64_t ld_in, const float* in, const int64_t* dst, int64_t n_in,
+                        int64_t ld_out, float* out, void* stream) {
+  if (n_cells <= 0 || ld_in <= 0 || n_in < 0 || ld_in < n_in || ld_out <= 0) return fail(BRIE_ERR_ARG, "bad shape");
+  if (!in || !out || (n_in > 0 && !dst)) return fail(BRIE_ERR_ARG, "null argument");
+  if (n_in == 0) return BRIE_OK;
+  scatter_columns_kernel<<<grid_1d(n_cells * n_in, 256), 256, 0, (cudaStream_t)stream>>>(in, ld_in, dst, n_cells,
+                                                                                        n_in, ld_out, out);
   BRIE_CUDA(cudaGetLastError());
   return BRIE_OK;
 }

@@ -67,6 +67,11 @@ struct StepArgs {
   const int32_t* blk_ids;
   int64_t blk_stride;
   int32_t n_blk[kMaxModels];
+  // Gathered sub-fit (brie_fit_buffers.event_ids): per-model column -> global event map and per-model
+  // count / length tiles.  Null / 0 = columns are events event_offset + column, tiles shared by all models.
+  const int32_t* ev_ids;   // (M, ld)
+  int64_t c_mstride;       // floats between the count tiles of consecutive models
+  int64_t eff_mstride;     // floats between the (3, ld) length tables of consecutive models
 };
 
 constexpr int kBlkCols = 8;   // events per compaction block = one 32-byte sector of every f32 array
@@ -317,12 +322,13 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     const bool ok = act != 0 && row < row_end;
     const int64_t off = ok ? row * a.ld + g0 : 0;
     const int64_t moff = ok ? (int64_t)m * plane + off : 0;
+    const int64_t coff = ok ? (int64_t)m * a.c_mstride + off : 0;
     const uint32_t dst = ring_lane + stage * (kRingArrays * TC * 4);
     cp_async_lane<EPL * 4>(dst + 0 * TC * 4, a.Zl + moff, ok);
     cp_async_lane<EPL * 4>(dst + 1 * TC * 4, a.Zs + moff, ok);
-    cp_async_lane<EPL * 4>(dst + 2 * TC * 4, a.c[0] + off, ok);
-    cp_async_lane<EPL * 4>(dst + 3 * TC * 4, a.c[1] + off, ok);
-    cp_async_lane<EPL * 4>(dst + 4 * TC * 4, has_c3 ? a.c[2] + off : a.c[0], ok && has_c3);
+    cp_async_lane<EPL * 4>(dst + 2 * TC * 4, a.c[0] + coff, ok);
+    cp_async_lane<EPL * 4>(dst + 3 * TC * 4, a.c[1] + coff, ok);
+    cp_async_lane<EPL * 4>(dst + 4 * TC * 4, has_c3 ? a.c[2] + coff : a.c[0], ok && has_c3);
     cp_async_lane<EPL * 4>(dst + 5 * TC * 4, a.aZ + moff, ok);
     cp_async_lane<EPL * 4>(dst + 6 * TC * 4, a.aZ + mplane + moff, ok);
     cp_async_lane<EPL * 4>(dst + 7 * TC * 4, a.aZ + 2 * mplane + moff, ok);
@@ -334,9 +340,13 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   // per-event constants
   if (threadIdx.x < TC) {
     const int64_t g = thread_col();
-    s_ev[threadIdx.x] = (uint32_t)(a.event_offset + g);
+    s_ev[threadIdx.x] = (a.ev_ids != nullptr && g < a.ld) ? (uint32_t)a.ev_ids[(int64_t)m * a.ld + g]
+                                                          : (uint32_t)(a.event_offset + g);
     float l1 = 1.f, l2 = 1.f, l3 = 0.f;
-    if (a.eff && g < a.ld) { l1 = a.eff[g]; l2 = a.eff[a.ld + g]; l3 = a.eff[2 * a.ld + g]; }
+    if (a.eff && g < a.ld) {
+      const float* ef = a.eff + (int64_t)m * a.eff_mstride;
+      l1 = ef[g]; l2 = ef[a.ld + g]; l3 = ef[2 * a.ld + g];
+    }
     s_L[0][threadIdx.x] = l1; s_L[1][threadIdx.x] = l2; s_L[2][threadIdx.x] = l3;
     if (LOSS) {  // log lengths for the constant part of the log-likelihood (0 * log 0 never occurs: eff > 0)
       s_L[3][threadIdx.x] = logf(l1); s_L[4][threadIdx.x] = logf(l2);

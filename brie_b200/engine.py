@@ -179,6 +179,9 @@ class FitEngine:
         self.n_iter = None
         self.losses = None
         self.loss_gene = None
+        self._lr = 0.0
+        self._sub_launches = 0      # launches made by gathered sub-fits on behalf of this engine
+        self.gather_rounds = 0      # extension rounds that ran on gathered sub-fits (diagnostic)
 
     def __del__(self):
         h = getattr(self, "h", None)
@@ -192,7 +195,7 @@ class FitEngine:
 
     @property
     def launch_count(self):
-        return int(self.lib.brie_fit_launch_count(self.h))
+        return int(self.lib.brie_fit_launch_count(self.h)) + self._sub_launches
 
     def kernel_timing(self, capacity):
         _lib.check(self.lib.brie_fit_kernel_timing(self.h, int(capacity)))
@@ -234,8 +237,15 @@ class FitEngine:
                 self.sigma_log[m, :n] = f(np.log(np.asarray(ob.sigma, np.float32).reshape(-1)))
 
     def begin_stage(self, lr):
+        self._lr = float(lr)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.brie_fit_begin_stage(self.h, float(lr), self._stream()))
+
+    def step_counters(self):
+        """(Adam step count of the open stage, RNG step word)."""
+        t, g = C.c_int64(), C.c_uint32()
+        _lib.check(self.lib.brie_fit_get_step(self.h, C.byref(t), C.byref(g)))
+        return t.value, g.value
 
     def run_steps(self, n, trace_slot0=-1):
         with torch.cuda.device(self.device):
@@ -288,6 +298,68 @@ class FitEngine:
         self._blk_ids = torch.from_numpy(ids).to(self.device)       # kept alive while the handle points at it
         _lib.check(self.lib.brie_fit_set_active_blocks(
             self.h, self._blk_ids.data_ptr(), stride, n_blk.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    # ------------------------------------------------------------------ gathered extension rounds
+    def _free_bytes(self):
+        free, _ = torch.cuda.mem_get_info(self.device)
+        return free + torch.cuda.memory_reserved(self.device) - torch.cuda.memory_allocated(self.device)
+
+    def run_steps_gathered(self, act, n_steps, force=False):
+        """One convergence-extension round (model_TFProb.py:250-258) of `n_steps` traced steps on the
+        events of the still-active reference batches only, act: (M, n_groups) bool.
+
+        The active columns of every model are gathered into dense per-model tiles (state, Adam
+        moments, counts, lengths), stepped as a sub-fit that keeps this engine's rows per CTA, RNG
+        counters (global event ids) and Adam step count, and scattered back together with their
+        loss trace -- so the round moves only bytes of active events, whatever the batch size
+        (a --batchSize 500000 batch is 5 events at 100k cells, 1 event at 1M cells: finer than the
+        32-byte sector the in-place block list can skip), and stays bit-identical to stepping the
+        whole shard with frozen events masked.  Sub-fits are cut to the free device memory and run
+        one after the other (events are independent).  Returns False, having done nothing, when the
+        fit has shared per-cell parameters, memory is short, or stepping in place over the 8-event
+        blocks that hold an active event (set_active_groups) moves no more bytes -- large batches,
+        e.g. 100 events at 5k cells, where the per-model count tiles of the gathered form (12 B per
+        model instead of 12 B shared) outweigh the few half-empty blocks: the caller then steps in
+        place.  `force` skips that cost comparison (tests)."""
+        if self.shared or self.target != "ELBO" or os.environ.get("BRIE_NO_GATHER"):
+            return False
+        M, Nc, L = self.M, self.Nc, self.n_layers
+        g = (np.arange(self.Ng) + self.event_offset) // self.group_size - self.first_group
+        cols = [np.flatnonzero(act[m, g]) for m in range(M)]
+        n_act = sum(len(c) for c in cols)
+        if n_act == 0 or n_act == M * self.Ng:
+            return False
+        if not force:
+            # bytes per cell and step: in place, every 8-event block with an active event moves whole
+            # (48 B state per model, 12 B counts shared by the models co-resident on the tile);
+            # gathered, only active events move but each model reads its own counts; plus the
+            # gather / scatter passes and ~15 ms of set-up per round
+            ev = np.zeros((M, _round_up(self.Ng, 8)), bool)
+            for m in range(M):
+                ev[m, cols[m]] = True
+            blk = ev.reshape(M, -1, 8).any(axis=2)
+            in_place = 8.0 * (48 * blk.sum() + 4 * L * blk.any(axis=0).sum())
+            gathered = n_act * (48 + 4 * L) * (1.0 + 3.0 / max(n_steps, 1)) + 1e11 / max(Nc * n_steps, 1)
+            if gathered > 0.9 * in_place:
+                return False
+        per_col = M * Nc * (L + 6) * 4 * 1.05 + M * (n_steps + 64) * 4
+        max_ld = int(0.85 * self._free_bytes() / per_col) // 32 * 32
+        nmax = max(len(c) for c in cols)
+        if max_ld < min(_round_up(nmax, 32), 256):
+            return False
+        n_parts = -(-nmax // max_ld)
+        parts = [np.array_split(c, n_parts) for c in cols]
+        t0, g0 = self.step_counters()
+        with torch.cuda.device(self.device):
+            for k in range(n_parts):
+                sub = _GatheredFit(self, [parts[m][k] for m in range(M)], n_steps)
+                sub.run(n_steps, self._lr, t0, g0)
+                sub.scatter_back()
+                self._sub_launches += sub.launches()
+                del sub
+            _lib.check(self.lib.brie_fit_resume_stage(self.h, self._lr, t0 + n_steps, g0 + n_steps))
+        self.gather_rounds += 1
+        return True
 
     def eval_loss_gene(self, n_eval=500, mc_size=1):
         """Mean of n_eval per-event loss evaluations (model_TFProb.py:261-264); each evaluation
@@ -351,8 +423,9 @@ class FitEngine:
                         active[m, g] = bool(cond) and n_iter[m, g] < max_iter
             if not active.any():
                 break
-            self.set_active_groups(active)
-            self.run_steps(add_iter, 0)
+            if not self.run_steps_gathered(active, add_iter):
+                self.set_active_groups(active)
+                self.run_steps(add_iter, 0)
             tr = self.group_trace(add_iter).astype(np.float32)
             for m in range(M):
                 for g in range(NG):
@@ -383,3 +456,122 @@ class FitEngine:
             out['intercept'] = self.intercept[m, :Ng].cpu().numpy().reshape(1, Ng)
             out['sigma'] = np.exp(self.sigma_log[m, :Ng].cpu().numpy()).reshape(1, Ng)
         return out
+
+
+class _GatheredFit:
+    """Sub-fit over gathered columns of a parent FitEngine (brie_fit_buffers.event_ids): model m's
+    column j is the parent's local event cols[m][j].  Holds its own dense tiles of the state, the
+    Adam moments, the counts and the lengths; shares Xc with the parent."""
+
+    def __init__(self, parent, cols, trace_cap):
+        p = self.p = parent
+        lib, dev, f32 = p.lib, p.device, torch.float32
+        M, Nc, L, Kc = p.M, p.Nc, p.n_layers, p.Kc
+        self.n = [len(c) for c in cols]
+        nmax = max(max(self.n), 1)
+        ld = self.ld = _round_up(nmax, 32)
+        self.n_moves = 0
+
+        d = _lib.FitDesc()
+        C.memmove(C.byref(d), C.byref(p.desc), C.sizeof(d))
+        d.n_events, d.ld, d.event_offset = nmax, ld, 0
+        d.trace_cap = trace_cap
+        d.rows_per_cta = p.sizes.rows_per_cta             # same association of the sums over cells
+        self.h = C.c_void_p()
+        _lib.check(lib.brie_fit_create(C.byref(d), C.byref(self.h)))
+        sz = _lib.FitSizes()
+        _lib.check(lib.brie_fit_get_sizes(self.h, C.byref(sz)))
+
+        self.idx = [torch.from_numpy(np.ascontiguousarray(c, dtype=np.int64)).to(dev) for c in cols]
+        ev = np.zeros((M, ld), np.int32)
+        act = np.zeros((M, ld), np.uint8)
+        for m, c in enumerate(cols):
+            ev[m, :len(c)] = c + p.event_offset
+            act[m, :len(c)] = 1
+        self.ev_ids = torch.from_numpy(ev).to(dev)
+        self.active = torch.from_numpy(act).to(dev)
+        self.counts = torch.empty((L, M, Nc, ld), dtype=f32, device=dev)
+        self.Z_loc = torch.empty((M, Nc, ld), dtype=f32, device=dev)
+        self.Z_std_log = torch.empty((M, Nc, ld), dtype=f32, device=dev)
+        self.adam_Z = torch.empty((4, M, Nc, ld), dtype=f32, device=dev)
+        self.Wc = torch.zeros((M, max(Kc, 1), ld), dtype=f32, device=dev)
+        self.intercept = torch.empty((M, ld), dtype=f32, device=dev)
+        self.sigma_log = torch.empty((M, ld), dtype=f32, device=dev)
+        n_mom = 2 * M * (Kc + 2) * ld                       # per-event moments come first (brie_abi.cu)
+        self.adam_small = torch.zeros(max(int(sz.adam_small_floats), n_mom, 4), dtype=f32, device=dev)
+        self.mom = self.adam_small[:n_mom].view(2, M, Kc + 2, ld)
+        self.eff = torch.empty((M, 3, ld), dtype=f32, device=dev) if p.eff is not None else None
+        self.loss_trace = torch.zeros((M, trace_cap, ld), dtype=f32, device=dev)
+        self.scratch = torch.empty(int(sz.scratch_bytes // 4) + 4, dtype=f32, device=dev)
+        self._move(gather=True)
+        if self.eff is not None:
+            for m in range(M):
+                self.eff[m, :, self.n[m]:] = 1.0          # padding columns: harmless lengths
+
+        b = _lib.FitBuffers()
+        for i in range(3):
+            b.counts[i] = self.counts[i].data_ptr() if i < L else None
+        b.counts_model_stride = Nc * ld
+        b.efflen3 = self.eff.data_ptr() if self.eff is not None else None
+        b.efflen_model_stride = 3 * ld if self.eff is not None else 0
+        b.event_ids = self.ev_ids.data_ptr()
+        b.Xc, b.Xg = p.Xc.data_ptr(), p.Xg.data_ptr()
+        b.Z_loc, b.Z_std_log, b.adam_Z = self.Z_loc.data_ptr(), self.Z_std_log.data_ptr(), self.adam_Z.data_ptr()
+        b.Wc, b.intercept, b.sigma_log = self.Wc.data_ptr(), self.intercept.data_ptr(), self.sigma_log.data_ptr()
+        b.Wg, b.adam_small = p.Wg.data_ptr(), self.adam_small.data_ptr()
+        b.active, b.loss_trace, b.scratch = self.active.data_ptr(), self.loss_trace.data_ptr(), self.scratch.data_ptr()
+        self.bufs = b
+        _lib.check(lib.brie_fit_bind(self.h, C.byref(b)))
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h is not None and h.value:
+            self.p.lib.brie_fit_destroy(h)
+            self.h = None
+
+    def launches(self):
+        return int(self.p.lib.brie_fit_launch_count(self.h)) + self.n_moves
+
+    def _pairs(self, m, inputs, trace_rows):
+        """(parent view, sub view) of model m, each rows x columns with the columns to move."""
+        p, Kc = self.p, self.p.Kc
+        pmom = p.adam_small[:2 * p.M * (Kc + 2) * p.ld].view(2, p.M, Kc + 2, p.ld)
+        out = [(p.Z_loc[m], self.Z_loc[m]), (p.Z_std_log[m], self.Z_std_log[m])]
+        out += [(p.adam_Z[k, m], self.adam_Z[k, m]) for k in range(4)]
+        if Kc > 0:
+            out.append((p.Wc[m], self.Wc[m]))
+        out += [(p.intercept[m:m + 1], self.intercept[m:m + 1]), (p.sigma_log[m:m + 1], self.sigma_log[m:m + 1])]
+        out += [(pmom[j, m], self.mom[j, m]) for j in range(2)]
+        if inputs:
+            out += [(p.counts[i], self.counts[i, m]) for i in range(p.n_layers)]
+            if self.eff is not None:
+                out.append((p.eff, self.eff[m]))
+        if trace_rows:
+            out.append((p.loss_trace[m, :trace_rows], self.loss_trace[m, :trace_rows]))
+        return out
+
+    def _move(self, gather, trace_rows=0):
+        """gather: parent -> sub (state, moments, counts, lengths); else scatter: sub -> parent (state,
+        moments, loss trace)."""
+        p, lib, st = self.p, self.p.lib, self.p._stream()
+        for m in range(p.M):
+            n, idx = self.n[m], self.idx[m].data_ptr()
+            if n == 0 and not gather:
+                continue
+            for big, small in self._pairs(m, gather, trace_rows):
+                assert big.is_contiguous() and small.is_contiguous()
+                rows = big.shape[0]
+                if gather:
+                    _lib.check(lib.brie_gather_events(rows, p.ld, big.data_ptr(), idx, n, self.ld, small.data_ptr(), st))
+                else:
+                    _lib.check(lib.brie_scatter_events(rows, self.ld, small.data_ptr(), idx, n, p.ld, big.data_ptr(), st))
+                self.n_moves += 1
+
+    def run(self, n_steps, lr, adam_t, global_step):
+        lib = self.p.lib
+        _lib.check(lib.brie_fit_resume_stage(self.h, float(lr), int(adam_t), int(global_step)))
+        _lib.check(lib.brie_fit_run_steps(self.h, int(n_steps), 0, self.p._stream()))
+        self.n_ran = int(n_steps)
+
+    def scatter_back(self):
+        self._move(gather=False, trace_rows=self.n_ran)

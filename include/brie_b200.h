@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define BRIE_ABI_VERSION 3
+#define BRIE_ABI_VERSION 4
 #define BRIE_MAX_MODELS 32
 #define BRIE_MAX_KC 16
 #define BRIE_MAX_KG 8
@@ -64,7 +64,9 @@ typedef struct brie_fit_desc {
   int32_t train_sigma;    /* sigma_log is a Variable (model_TFProb.py:73-78) */
   int32_t trace_cap;      /* slots in loss_trace per model */
   int32_t target;         /* BRIE_TARGET_ELBO (model_TFProb.py:206-211) or BRIE_TARGET_MARGINLIK (:202-205) */
-  int32_t reserved0;
+  int32_t rows_per_cta;   /* 0: library picks the cell rows per CTA; > 0: use this value (a gathered sub-fit of
+                             brie_fit_bind's event_ids keeps its parent's value, so the float32 partial sums over
+                             cells associate the same way and its results stay bit-identical to the parent's) */
   int32_t model_id[BRIE_MAX_MODELS]; /* RNG model word of each batched model */
   uint32_t xc_mask[BRIE_MAX_MODELS]; /* bit k set: column k of Xc[model] is a real covariate */
 } brie_fit_desc;
@@ -95,6 +97,17 @@ typedef struct brie_fit_buffers {
   const uint8_t* active;  /* (M, ld): 1 = this model still optimises this event */
   float* loss_trace;      /* (M, trace_cap, ld): per-step per-event loss (pre-update) */
   void* scratch;
+  /* Gathered sub-fit (the convergence-extension rounds of model_TFProb.py:250-258 on the events whose reference
+   * batch has not converged yet, physically compacted so that every 32-byte sector moved holds active events).
+   * Each model then has its OWN column -> event map and therefore its own gathered count / length tiles:
+   *  event_ids (M, ld) int32: global event id of every column (the RNG counter word), NULL = event_offset + column;
+   *  counts_model_stride: floats between the count tiles of consecutive models, 0 = all models share one tile;
+   *  efflen_model_stride: likewise for efflen3 ((3, ld) per model), 0 = shared.
+   * Only the step entry points work on such a fit (Kg = 0, cell_mode = 0, target ELBO); results go back with
+   * brie_scatter_events. */
+  const int32_t* event_ids;
+  int64_t counts_model_stride;
+  int64_t efflen_model_stride;
 } brie_fit_buffers;
 
 typedef struct brie_fit brie_fit; /* opaque */
@@ -118,6 +131,12 @@ int brie_fit_init_params(brie_fit* fit, float intercept_const, float sigma_const
 /* Replaces `tf.optimizers.Adam(learning_rate=lr)` (model_TFProb.py:237): zero
  * all Adam moments and reset the step count t of every model. */
 int brie_fit_begin_stage(brie_fit* fit, float lr, void* stream);
+
+/* Continue an optimiser that already took `adam_t` steps in its stage (the extension rounds keep using the last
+ * stage's optimizer, model_TFProb.py:255): like brie_fit_begin_stage but the Adam moments are left as they are,
+ * the Adam step count starts at adam_t and the RNG step word at global_step.  brie_fit_get_step reads both. */
+int brie_fit_resume_stage(brie_fit* fit, float lr, int64_t adam_t, uint32_t global_step);
+int brie_fit_get_step(const brie_fit* fit, int64_t* adam_t, uint32_t* global_step);
 
 /* Replaces `tfp.math.minimize(loss_fn, num_steps, optimizer)` (model_TFProb.py:239,
  * 255): n_steps fused ELBO forward + backward + Adam steps (get_loss :194-211,
@@ -227,6 +246,11 @@ int brie_gene_stats(int64_t n_cells, int64_t ld, const float* c1, const float* c
  * host round trip): out[r, j] = in[r, src[j]] for j < n_out, zero padding up to ld_out. */
 int brie_gather_events(int64_t n_cells, int64_t ld_in, const float* in, const int64_t* src,
                        int64_t n_out, int64_t ld_out, float* out, void* stream);
+
+/* Inverse of brie_gather_events: out[r, dst[j]] = in[r, j] for j < n_in; other columns of `out` are untouched.
+ * dst entries must be distinct. */
+int brie_scatter_events(int64_t n_cells, int64_t ld_in, const float* in, const int64_t* dst,
+                        int64_t n_in, int64_t ld_out, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -205,3 +205,83 @@ def test_active_block_compaction_is_bit_identical(Nc, Ng, Kc, group, monkeypatch
             assert np.array_equal(tr_a[m][act_a[m]], tr_b[m][act_b[m]])
     # the compacted rounds did move the active events
     assert not torch.equal(a['Z_loc'], before)
+
+
+@pytest.mark.parametrize("Nc,Ng,Kc,group,split", [(300, 1000, 1, 100, False), (520, 333, 9, 7, False),
+                                                  (64, 77, 0, 5, False), (40, 2100, 2, 1, True),
+                                                  (700, 640, 4, 3, True)])
+def test_gathered_extension_round_is_bit_identical(Nc, Ng, Kc, group, split, monkeypatch):
+    """Extension rounds on physically gathered columns (FitEngine.run_steps_gathered: per-model dense
+    sub-fits of the still-active events, brie_fit_buffers.event_ids) against stepping the whole shard
+    in place with the frozen events masked: state, Adam moments, small parameters and the loss trace
+    of the active groups agree bit for bit; frozen events are untouched; the step counters (Adam t,
+    RNG step word) advance the same; cutting the round into several sub-fits (memory-bound case)
+    changes nothing."""
+    from brie_b200.engine import FitEngine
+    data, effLen, Xc, _ = make_problem(Nc, Ng, Kc, 0, True, 3, seed=8)
+    add_pseudo_count(data, np.float32(0.01))
+    masks = [list(range(Kc)), list(range(1, Kc))] if Kc > 0 else [[], []]
+
+    def run(gathered):
+        monkeypatch.setenv("BRIE_NO_COMPACT", "1")
+        eng = FitEngine(data, effLen=effLen, Xc=Xc, masks=masks, model_ids=[0, 1], MC_size=3, seed=12,
+                        trace_cap=8, group_size=group, event_offset=11 * group, n_events_total=Ng + 30 * group)
+        if split:      # pretend only ~1/3 of the widest active set fits the free memory
+            per_col = 2 * Nc * 9 * 4 * 1.05 + 2 * (3 + 64) * 4          # run_steps_gathered's own estimate
+            monkeypatch.setattr(eng, "_free_bytes", lambda: int(per_col * 300 / 0.85))   # room for 288 columns
+        eng.init_params()
+        eng.begin_stage(0.01)
+        eng.run_steps(4)
+        before = eng.Z_loc.clone()
+        outs = []
+        for frac in (0.3, 0.05):
+            act = np.random.default_rng(int(frac * 100) + 1).random((2, eng.n_groups)) < frac
+            act[1, 0] = True
+            if frac < 0.1:
+                act[0, :] = False                       # a model with nothing left to do
+            if gathered:
+                assert eng.run_steps_gathered(act, 3, force=True)
+            else:
+                eng.set_active_groups(act)
+                eng.run_steps(3, 0)
+            outs.append((act, eng.group_trace(3)))
+        eng.set_active_groups(np.ones((2, eng.n_groups), bool))
+        eng.run_steps(2, 0)
+        torch.cuda.synchronize()
+        st = dict(Z_loc=eng.Z_loc.clone(), Z_std_log=eng.Z_std_log.clone(), adam=eng.adam_Z.clone(),
+                  Wc=eng.Wc.clone(), b=eng.intercept.clone(), tau=eng.sigma_log.clone(),
+                  small=eng.adam_small.clone(), trace=eng.loss_trace[:, :2].clone())
+        return st, outs, before, eng
+
+    a, outs_a, before, eng_a = run(True)
+    b, outs_b, _, eng_b = run(False)
+    assert eng_a.gather_rounds == 2 and eng_b.gather_rounds == 0
+    assert eng_a.step_counters() == eng_b.step_counters() == (12, 12)
+    for k in a:
+        assert torch.equal(a[k][..., :Ng], b[k][..., :Ng]) if a[k].dim() > 1 else torch.equal(a[k], b[k]), k
+    for (act_a, tr_a), (act_b, tr_b) in zip(outs_a, outs_b):
+        assert np.array_equal(act_a, act_b)
+        for m in range(2):
+            assert np.array_equal(tr_a[m][act_a[m]], tr_b[m][act_b[m]])
+    assert not torch.equal(a['Z_loc'], before)
+    assert eng_a.launch_count > eng_b.launch_count    # gathers / scatters are counted
+
+
+def test_gathered_round_declines_when_it_cannot_help():
+    """Shared per-cell parameters, everything still active, or no memory: run_steps_gathered does
+    nothing and says so (the caller steps in place)."""
+    from brie_b200.engine import FitEngine
+    data, effLen, Xc, Xg = make_problem(50, 64, 1, 2, True, 3, seed=2)
+    add_pseudo_count(data, np.float32(0.01))
+    eng = FitEngine(data, effLen=effLen, Xc=Xc, Xg=Xg, MC_size=2, seed=1, trace_cap=4, group_size=8)
+    eng.init_params(); eng.begin_stage(0.01)
+    assert not eng.run_steps_gathered(np.zeros((1, eng.n_groups), bool), 2, force=True)   # Kg > 0: shared Wg
+    eng = FitEngine(data, effLen=effLen, Xc=Xc, MC_size=2, seed=1, trace_cap=4, group_size=8)
+    eng.init_params(); eng.begin_stage(0.01)
+    assert not eng.run_steps_gathered(np.ones((1, eng.n_groups), bool), 2, force=True)    # all active
+    assert not eng.run_steps_gathered(np.zeros((1, eng.n_groups), bool), 2, force=True)   # nothing active
+    act = np.zeros((1, eng.n_groups), bool); act[0, 1] = True
+    assert not eng.run_steps_gathered(act, 2)            # 8-event batches = whole blocks: in place is as cheap
+    eng._free_bytes = lambda: 1000
+    assert not eng.run_steps_gathered(act, 2, force=True)                                 # no memory
+    assert eng.step_counters() == (0, 0)
