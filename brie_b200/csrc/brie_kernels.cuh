@@ -236,24 +236,26 @@ constexpr int kRingArrays = 9;    // Z_loc, Z_std_log, c1, c2, c3, m_loc, v_loc,
 constexpr int kRingStages = 2;
 __host__ __device__ constexpr int step_tile_cols(int KC) { return 32 * step_epl(KC); }
 // Per-event constants of a column tile (Wc rows, Xg columns, intercept, sigma_log, 1/sigma^2) stay in
-// registers for narrow designs; wider ones keep them in shared memory and re-read them every row, so
-// they are not live across the Monte-Carlo phase (no spills).  Measured on one box (profiles/
-// r1_ab_smem_consts.md): C3 with loss trace +11 %, C4 +10 % / +23 %, Kc 15 +9 %; only Kc <= 4 without
-// gene features and without the loss trace is faster from registers (C3: 4 %).
+// registers for narrow designs; wider ones (Kc + Kg >= 3) keep them in shared memory and re-read them
+// every row, so they are not live across the Monte-Carlo phase (no spills).  A/B on one box
+// (profiles/r1_ab_smem_consts.md, r1_ab_row_consts.md): C3 with loss trace +11 %, C4 +10 % / +23 %,
+// Kc 15 +9 %; C3 without the loss trace runs 1 % slower from shared memory but spills from registers.
 #ifndef BRIE_SMEM_CONSTS_MODE
-#define BRIE_SMEM_CONSTS_MODE 0   // A/B aid (scripts/ab.sh): 1 = shared memory whenever Kc + Kg >= 3, 2 = never
+#define BRIE_SMEM_CONSTS_MODE 0   // A/B aid (scripts/ab.sh): 1 = registers for Kc <= 4 without Kg / loss trace, 2 = never
 #endif
 __host__ __device__ constexpr bool step_consts_in_smem(int KC, int KG, bool LOSS) {
-  if (BRIE_SMEM_CONSTS_MODE == 1) return KC + KG >= 3;
+  if (BRIE_SMEM_CONSTS_MODE == 1) return KC + KG >= 3 && !(KG == 0 && KC <= 4 && !LOSS);
   if (BRIE_SMEM_CONSTS_MODE == 2) return false;
-  return KC + KG >= 3 && !(KG == 0 && KC <= 4 && !LOSS);
+  return KC + KG >= 3;
 }
 __host__ __device__ constexpr int step_n_consts(int KC, int KG, bool CELL, bool LOSS) {
   return step_consts_in_smem(KC, KG, LOSS) ? KC + KG + (CELL ? 0 : 3) : 0;
 }
+constexpr int kRowConstSlots = 32;   // per warp and ring stage: Xc[c, :], Wg[c, :], per-cell intercept / sigma_log of the row
 __host__ __device__ constexpr int step_smem_bytes(int KC, int KG, bool CELL, bool LOSS) {
   return (kWarps * kRingStages * kRingArrays + kWarps * kQueueFields + 7 + step_n_consts(KC, KG, CELL, LOSS)) *
-         step_tile_cols(KC) * 4;
+             step_tile_cols(KC) * 4 +
+         kWarps * kRingStages * kRowConstSlots * 4;
 }
 
 template <int KC, int KG, bool CELL, bool LOSS>
@@ -306,6 +308,11 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
                                                    kWarps * kQueueFields * TC);
   uint32_t* s_ev = reinterpret_cast<uint32_t*>(s_L + 6);   // global event id of each tile column (RNG counter word)
   float(*s_k)[TC] = s_L + 7;                // kSm: rows Wc[0..KC), Xg[0..KG), then (gene mode) b, tau, 1/sigma^2
+  constexpr int NRC = KC + KG + (CELL ? 2 : 0);   // per-row (cell) constants: Xc[c, :], Wg[c, :], b[c], tau[c]
+  static_assert(NRC <= kRowConstSlots, "row constants must fit one slot per lane");
+  float* s_rc = smem + (kWarps * kRingStages * kRingArrays + kWarps * kQueueFields + 7 +
+                        step_n_consts(KC, KG, CELL, LOSS)) * TC +
+                warp * (kRingStages * kRowConstSlots);
 
   const int64_t row_begin = (int64_t)chunk * a.rows_per_cta;
   const int64_t row_end = min(row_begin + (int64_t)a.rows_per_cta, a.Nc);
@@ -318,6 +325,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   // Lanes whose events are all frozen (converged reference batches) copy nothing: their ring slots are
   // zero-filled, they compute on zeros and store nothing, so a partly active tile only pays for the
   // 32-byte sectors that hold active events.
+  const uint32_t rc_lane = (uint32_t)__cvta_generic_to_shared(s_rc) + lane * 4;
   auto issue_row = [&](int64_t row, int stage) {
     const bool ok = act != 0 && row < row_end;
     const int64_t off = ok ? row * a.ld + g0 : 0;
@@ -333,6 +341,19 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     cp_async_lane<EPL * 4>(dst + 6 * TC * 4, a.aZ + mplane + moff, ok);
     cp_async_lane<EPL * 4>(dst + 7 * TC * 4, a.aZ + 2 * mplane + moff, ok);
     cp_async_lane<EPL * 4>(dst + 8 * TC * 4, a.aZ + 3 * mplane + moff, ok);
+    if (NRC > 0) {
+      // The row's warp-uniform constants ride in the same commit group, one float per lane.  (As plain
+      // loads issued a row ahead they shared a scoreboard with the tile constants loaded before the loop,
+      // and the first use of those waited for the prefetch every row: 23 % of the stall samples.)
+      const bool okc = lane < NRC && row < row_end;
+      const int64_t mr = (int64_t)m * a.Nc + (okc ? row : 0);
+      const float* src = a.Xc;
+      if (lane < KC) src = a.Xc + mr * KC + lane;
+      else if (lane < KC + KG) src = a.Wg + mr * KG + (lane - KC);
+      else if (CELL && lane == KC + KG) src = a.b + mr;
+      else if (CELL) src = a.tau + mr;
+      cp_async_lane<4>(rc_lane + stage * (kRowConstSlots * 4), src, okc);
+    }
     cp_async_commit();
   };
   issue_row(row_begin + warp, 0);
@@ -408,33 +429,22 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   const uint32_t stream0 = brie_stream_word(BRIE_PHASE_TRAIN, (uint32_t)a.model_id[m], 0u);
   const uint32_t lt_mask = (1u << lane) - 1u;
 
-  // per-row (cell) constants are warp-uniform loads; fetch them one row ahead so their latency
-  // overlaps the current row's work like the ring does for the big arrays
-  float xc_n[KC > 0 ? KC : 1], wg_n[KG > 0 ? KG : 1], b_n = 0.f, tau_n = 0.f;
-  auto load_row_consts = [&](int64_t row) {
-    const int64_t r = row < row_end ? row : row_end - 1;
-#pragma unroll
-    for (int k = 0; k < KC; ++k) xc_n[k] = __ldg(a.Xc + ((int64_t)m * a.Nc + r) * KC + k);
-#pragma unroll
-    for (int k = 0; k < KG; ++k) wg_n[k] = __ldg(a.Wg + ((int64_t)m * a.Nc + r) * KG + k);
-    if (CELL) {
-      b_n = __ldg(a.b + (int64_t)m * a.Nc + r);
-      tau_n = __ldg(a.tau + (int64_t)m * a.Nc + r);
-    }
-  };
-  if (row_begin + warp < row_end) load_row_consts(row_begin + warp);
-
   int stage = 0;
   for (int64_t row = row_begin + warp; row < row_end; row += kWarps, stage ^= 1) {
-    float xc[KC > 0 ? KC : 1], wg[KG > 0 ? KG : 1];
-#pragma unroll
-    for (int k = 0; k < KC; ++k) xc[k] = xc_n[k];
-#pragma unroll
-    for (int k = 0; k < KG; ++k) wg[k] = wg_n[k];
-    const float b_row = b_n, tau_row = tau_n;
     issue_row(row + kWarps, stage ^ 1);   // prefetch the next row (zero-size copies past the end)
-    load_row_consts(row + kWarps);
     cp_async_wait<1>();                   // this row's group has landed
+    float xc[KC > 0 ? KC : 1], wg[KG > 0 ? KG : 1];
+    float b_row = 0.f, tau_row = 0.f;
+    if (NRC > 0) {
+      __syncwarp();                       // the row constants were copied by other lanes
+      const float* rc = s_rc + stage * kRowConstSlots;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) xc[k] = rc[k];
+#pragma unroll
+      for (int k = 0; k < KG; ++k) wg[k] = rc[KC + k];
+      if (CELL) { b_row = rc[KC + KG]; tau_row = rc[KC + KG + 1]; }
+      __syncwarp();                       // all lanes have read them before any lane's next prefetch overwrites the slot two rows on
+    }
     const Vec* st = reinterpret_cast<const Vec*>(s_ring + stage * (kRingArrays * TC)) + lane;
     float mu[EPL], lam[EPL], c1[EPL], c2[EPL], c3[EPL];
     vec_get<EPL>(st[0 * 32], mu);
