@@ -308,6 +308,14 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
                                                    kWarps * kQueueFields * TC);
   uint32_t* s_ev = reinterpret_cast<uint32_t*>(s_L + 6);   // global event id of each tile column (RNG counter word)
   float(*s_k)[TC] = s_L + 7;                // kSm: rows Wc[0..KC), Xg[0..KG), then (gene mode) b, tau, 1/sigma^2
+  // Gene-feature slots are stored XOR-permuted per lane (slot i of lane L holds feature i ^ pk(L), pk = the top
+  // log2(KG) lane bits reversed into a feature index) so that the per-cell reduction over the 32 lanes of
+  // d loss / d Wg[c, :] is a halving butterfly without selects (see the end of the row loop).
+  constexpr int KGB = KG == 8 ? 3 : (KG == 4 ? 2 : 0);
+  static_assert(KG == 0 || (1 << KGB) == KG, "KG must be a power of two");
+  int pk = 0;
+#pragma unroll
+  for (int t = 0; t < KGB; ++t) pk |= ((lane >> (4 - t)) & 1) << (KGB - 1 - t);
   constexpr int NRC = KC + KG + (CELL ? 2 : 0);   // per-row (cell) constants: Xc[c, :], Wg[c, :], b[c], tau[c]
   static_assert(NRC <= kRowConstSlots, "row constants must fit one slot per lane");
   float* s_rc = smem + (kWarps * kRingStages * kRingArrays + kWarps * kQueueFields + 7 +
@@ -409,7 +417,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
 #pragma unroll
-      for (int k = 0; k < KG; ++k) xg[k][j] = (g0 + j) < a.Ng ? a.Xg[(g0 + j) * KG + k] : 0.f;
+      for (int k = 0; k < KG; ++k) xg[k][j] = (g0 + j) < a.Ng ? a.Xg[(g0 + j) * KG + (k ^ pk)] : 0.f;
     }
     if (!CELL) {
       vec_get<EPL>(*reinterpret_cast<const Vec*>(a.b + (int64_t)m * a.ld + g0), bb);
@@ -441,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 #pragma unroll
       for (int k = 0; k < KC; ++k) xc[k] = rc[k];
 #pragma unroll
-      for (int k = 0; k < KG; ++k) wg[k] = rc[KC + k];
+      for (int k = 0; k < KG; ++k) wg[k] = rc[KC + (k ^ pk)];
       if (CELL) { b_row = rc[KC + KG]; tau_row = rc[KC + KG + 1]; }
       __syncwarp();                       // all lanes have read them before any lane's next prefetch overwrites the slot two rows on
     }
@@ -463,7 +471,8 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 #pragma unroll
       for (int k = 0; k < KC; ++k) vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[k][lane * EPL]), wc[k]);
 #pragma unroll
-      for (int k = 0; k < KG; ++k) vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + k][lane * EPL]), xg[k]);
+      for (int k = 0; k < KG; ++k)
+        vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + (k ^ pk)][lane * EPL]), xg[k]);
       if (!CELL) {
         vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + KG][lane * EPL]), bb);
         vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + KG + 1][lane * EPL]), tau);
@@ -597,10 +606,29 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       __stcs(reinterpret_cast<Vec*>(a.aZ + 3 * mplane + moff), vec_make<EPL>(v2));
     }
     if (NCELL > 0) {
+      float* pc = a.part_cell + (((int64_t)tile * a.M + m) * a.Nc + row) * NCELL;
+      if (KG > 0) {
+        // Halving butterfly: slot i of this lane holds feature i ^ pk, so at every step all lanes keep
+        // the lower half of their slots and hand the upper half to the partner that keeps those features
+        // (no selects); KG - 1 + log2(32 / KG) shuffles instead of 5 KG.
 #pragma unroll
-      for (int i = 0; i < NCELL; ++i) {
-        const float s = warp_sum(cacc[i]);
-        if (lane == 0) a.part_cell[(((int64_t)tile * a.M + m) * a.Nc + row) * NCELL + i] = s;
+        for (int t = 0; t < KGB; ++t) {
+          const int H = KG >> (t + 1);
+#pragma unroll
+          for (int i = 0; i < H; ++i) cacc[i] += __shfl_xor_sync(0xffffffffu, cacc[H + i], 16 >> t);
+        }
+        float s = cacc[0];
+#pragma unroll
+        for (int o = 16 >> KGB; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((lane & ((32 >> KGB) - 1)) == 0) pc[pk] = s;
+      }
+      if (CELL) {  // d/d intercept and d/d sigma_log of the cell: two values, one per half-warp after the first step
+        const bool hi = (lane & 16) != 0;
+        const float keep = hi ? cacc[KG + 1] : cacc[KG], send = hi ? cacc[KG] : cacc[KG + 1];
+        float s = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if ((lane & 15) == 0) pc[KG + (hi ? 1 : 0)] = s;
       }
     }
   }
