@@ -343,20 +343,35 @@ class FitEngine:
             if gathered > 0.9 * in_place:
                 return False
         per_col = M * Nc * (L + 6) * 4 * 1.05 + M * (n_steps + 64) * 4
-        max_ld = int(0.85 * self._free_bytes() / per_col) // 32 * 32
+        max_ld = int(0.8 * self._free_bytes() / per_col) // 32 * 32
         nmax = max(len(c) for c in cols)
         if max_ld < min(_round_up(nmax, 32), 256):
             return False
         n_parts = -(-nmax // max_ld)
-        parts = [np.array_split(c, n_parts) for c in cols]
+        todo = [[np.array_split(c, n_parts)[k] for c in cols] for k in range(n_parts)]
         t0, g0 = self.step_counters()
+        done = 0
         with torch.cuda.device(self.device):
-            for k in range(n_parts):
-                sub = _GatheredFit(self, [parts[m][k] for m in range(M)], n_steps)
+            while todo:
+                part = todo.pop(0)
+                try:
+                    sub = _GatheredFit(self, part, n_steps)
+                except torch.cuda.OutOfMemoryError:
+                    # the estimate was too optimistic (allocator fragmentation): nothing has been touched by this
+                    # part yet: if no part has run leave the whole round to the in-place walk, else halve the part
+                    sub = None
+                    torch.cuda.empty_cache()
+                    if done == 0:
+                        return False
+                    if max(len(c) for c in part) <= 32:
+                        raise
+                    todo[:0] = [[np.array_split(c, 2)[h] for c in part] for h in range(2)]
+                    continue
                 sub.run(n_steps, self._lr, t0, g0)
                 sub.scatter_back()
                 self._sub_launches += sub.launches()
                 del sub
+                done += 1
             _lib.check(self.lib.brie_fit_resume_stage(self.h, self._lr, t0 + n_steps, g0 + n_steps))
         self.gather_rounds += 1
         return True

@@ -228,7 +228,7 @@ def test_gathered_extension_round_is_bit_identical(Nc, Ng, Kc, group, split, mon
                         trace_cap=8, group_size=group, event_offset=11 * group, n_events_total=Ng + 30 * group)
         if split:      # pretend only ~1/3 of the widest active set fits the free memory
             per_col = 2 * Nc * 9 * 4 * 1.05 + 2 * (3 + 64) * 4          # run_steps_gathered's own estimate
-            monkeypatch.setattr(eng, "_free_bytes", lambda: int(per_col * 300 / 0.85))   # room for 288 columns
+            monkeypatch.setattr(eng, "_free_bytes", lambda: int(per_col * 300 / 0.8))    # room for 288 columns
         eng.init_params()
         eng.begin_stage(0.01)
         eng.run_steps(4)
@@ -285,3 +285,48 @@ def test_gathered_round_declines_when_it_cannot_help():
     eng._free_bytes = lambda: 1000
     assert not eng.run_steps_gathered(act, 2, force=True)                                 # no memory
     assert eng.step_counters() == (0, 0)
+
+
+def test_gathered_round_survives_out_of_memory(monkeypatch):
+    """The sub-fit size is an estimate; if an allocation fails the round must not die half done: before
+    anything ran it is handed back to the in-place walk, later the failing part is halved and retried --
+    with the same result bit for bit."""
+    from brie_b200 import engine as E
+    Nc, Ng, group = 200, 960, 3
+    data, effLen, Xc, _ = make_problem(Nc, Ng, 1, 0, True, 3, seed=9)
+    add_pseudo_count(data, np.float32(0.01))
+
+    def fresh():
+        eng = E.FitEngine(data, effLen=effLen, Xc=Xc, masks=[[0], []], MC_size=3, seed=4, trace_cap=4, group_size=group)
+        eng.init_params(); eng.begin_stage(0.01); eng.run_steps(3)
+        return eng
+
+    act = np.random.default_rng(0).random((2, Ng // group)) < 0.45      # 400+ active events per model
+    ref = fresh()
+    assert ref.run_steps_gathered(act, 2, force=True)
+
+    real_init, calls = E._GatheredFit.__init__, []
+
+    def flaky(self, parent, cols, trace_cap):
+        calls.append(max(len(c) for c in cols))
+        if len(calls) in fail_on:
+            raise torch.cuda.OutOfMemoryError("injected")
+        real_init(self, parent, cols, trace_cap)
+
+    monkeypatch.setattr(E._GatheredFit, "__init__", flaky)
+    fail_on = {1}
+    eng = fresh()
+    before = eng.Z_loc.clone()
+    assert not eng.run_steps_gathered(act, 2, force=True) and eng.step_counters() == (3, 3)
+    assert torch.equal(eng.Z_loc, before)
+    calls.clear()
+    fail_on = {2}
+    eng = fresh()
+    per_col = 2 * Nc * 9 * 4 * 1.05 + 2 * (2 + 64) * 4
+    monkeypatch.setattr(eng, "_free_bytes", lambda: int(per_col * 270 / 0.8))      # 256 columns at a time: two parts
+    assert eng.run_steps_gathered(act, 2, force=True)
+    assert len(calls) >= 4 and calls[2] < calls[1]                                 # the second part was halved
+    torch.cuda.synchronize()
+    for a, b in ((eng.Z_loc, ref.Z_loc), (eng.adam_Z, ref.adam_Z), (eng.Wc, ref.Wc), (eng.loss_trace, ref.loss_trace)):
+        assert torch.equal(a, b)
+    assert eng.step_counters() == ref.step_counters() == (5, 5)
