@@ -231,7 +231,7 @@ __device__ __forceinline__ void cp_async_lane(uint32_t dst_smem, const void* src
 //     samples (Philox + Box-Muller + likelihood gradient) -- zero-count elements,
 //     80-87 % of real data, cost nothing here and the lanes stay converged;
 //   C (dense): owners read their MC sums back, Adam-update and store (16 B stores at EPL = 4).
-constexpr int kQueueFields = 6;   // mu, s, c1, c2, c3, column  ->  results overwrite c1, c2, c3
+constexpr int kQueueFields = 1;   // tile column of the element; its data is read from, and its results written to, the row's ring slots
 constexpr int kRingArrays = 9;    // Z_loc, Z_std_log, c1, c2, c3, m_loc, v_loc, m_std, v_std
 constexpr int kRingStages = 2;
 __host__ __device__ constexpr int step_tile_cols(int KC) { return 32 * step_epl(KC); }
@@ -302,8 +302,8 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 
   extern __shared__ __align__(128) float smem[];
   float* s_ring = smem + warp * (kRingStages * kRingArrays * TC);
-  float(*q)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * kRingArrays * TC +
-                                                 warp * kQueueFields * TC);
+  uint32_t* q = reinterpret_cast<uint32_t*>(smem + kWarps * kRingStages * kRingArrays * TC +
+                                            warp * kQueueFields * TC);
   float(*s_L)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * kRingArrays * TC +
                                                    kWarps * kQueueFields * TC);
   uint32_t* s_ev = reinterpret_cast<uint32_t*>(s_L + 6);   // global event id of each tile column (RNG counter word)
@@ -443,8 +443,8 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     cp_async_wait<1>();                   // this row's group has landed
     float xc[KC > 0 ? KC : 1], wg[KG > 0 ? KG : 1];
     float b_row = 0.f, tau_row = 0.f;
+    __syncwarp();                         // other lanes read this lane's copies (row constants, Monte-Carlo items)
     if (NRC > 0) {
-      __syncwarp();                       // the row constants were copied by other lanes
       const float* rc = s_rc + stage * kRowConstSlots;
 #pragma unroll
       for (int k = 0; k < KC; ++k) xc[k] = rc[k];
@@ -532,45 +532,44 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     if (n_items > 0) {
 #pragma unroll
       for (int j = 0; j < EPL; ++j) base += __popc(bal[j] & lt_mask);
-      int pos = base;
+      // The queue holds tile columns only.  The row's Z_loc, Z_std_log and counts are still in this stage of
+      // the ring, so whichever lane takes an item reads them from there and leaves the Monte-Carlo sums in the
+      // element's own count slots; an element without reads has zeros in those slots (counts are >= 0), so the
+      // owners subtract their slots unconditionally afterwards.
 #pragma unroll
-      for (int j = 0; j < EPL; ++j) {
-        if ((nz >> j) & 1u) {
-          q[0][pos] = mu[j];
-          q[1][pos] = fast_exp(lam[j]);
-          q[2][pos] = c1[j];
-          q[3][pos] = c2[j];
-          q[4][pos] = c3[j];
-          q[5][pos] = __int_as_float(lane * EPL + j);
-          ++pos;
-        }
-      }
+      for (int j = 0; j < EPL; ++j)
+        if ((nz >> j) & 1u) q[base + __popc(nz & ((1u << j) - 1u))] = (uint32_t)(lane * EPL + j);
       __syncwarp();
+      float* rs = s_ring + stage * (kRingArrays * TC);
       for (int k = lane; k < n_items; k += 32) {
-        const float imu = q[0][k], is = q[1][k], ic1 = q[2][k], ic2 = q[3][k], ic3 = q[4][k];
+        const int col = (int)q[k];
+        const float imu = rs[col], is = fast_exp(rs[TC + col]);
+        const float ic1 = rs[2 * TC + col], ic2 = rs[3 * TC + col], ic3 = rs[4 * TC + col];
         const float in = ic1 + ic2 + ic3;
-        const int col = __float_as_int(q[5][k]);
         const float l1 = s_L[0][col], l2 = s_L[1][col], l3 = s_L[2][col];
         float gs, ge, ls;
         mc_samples<LOSS>(imu, is, ic1, ic2, in, l1, l2, l3, l1 - l2, a.S, s_ev[col], (uint32_t)row,
                          a.step, stream0, a.seed, gs, ge, ls);
-        q[2][k] = gs * a.inv_S;
-        q[3][k] = ge * is * a.inv_S;
+        rs[2 * TC + col] = gs * a.inv_S;
+        rs[3 * TC + col] = ge * is * a.inv_S;
         if (LOSS)
-          q[4][k] = fmaf(ls, a.inv_S, fmaf(ic1, s_L[3][col], fmaf(ic2, s_L[4][col], ic3 * s_L[5][col])));
+          rs[4 * TC + col] = fmaf(ls, a.inv_S, fmaf(ic1, s_L[3][col], fmaf(ic2, s_L[4][col], ic3 * s_L[5][col])));
       }
       __syncwarp();
-      pos = base;
+      float r1[EPL], r2[EPL];
+      vec_get<EPL>(st[2 * 32], r1);
+      vec_get<EPL>(st[3 * 32], r2);
 #pragma unroll
       for (int j = 0; j < EPL; ++j) {
-        if ((nz >> j) & 1u) {
-          gmu[j] -= q[2][pos];
-          glam[j] -= q[3][pos];
-          if (LOSS) acc[T::kLoss][j] -= q[4][pos];
-          ++pos;
-        }
+        gmu[j] -= r1[j];
+        glam[j] -= r2[j];
       }
-      __syncwarp();  // queue is reused by the next row
+      if (LOSS) {
+        float r3[EPL];
+        vec_get<EPL>(st[4 * 32], r3);
+#pragma unroll
+        for (int j = 0; j < EPL; ++j) acc[T::kLoss][j] -= r3[j];
+      }
     }
 
     // ---- phase C: Adam on Z_loc / Z_std_log, clip, store ----
