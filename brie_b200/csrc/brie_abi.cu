@@ -162,6 +162,13 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
     const int64_t target = 148 * 2 * 10;
     while (rows > 8 && (int64_t)d.n_models * n_tiles * ceil_div(d.n_cells, rows) < target) rows >>= 1;
   }
+  // the step kernel addresses a CTA's elements with 32-bit offsets (local row) * ld + column
+  while (d.rows_per_cta == 0 && rows > 8 && (int64_t)rows * d.ld >= ((int64_t)1 << 31)) rows >>= 1;
+  if ((int64_t)rows * d.ld >= ((int64_t)1 << 31)) {
+    delete f;
+    return fail(BRIE_ERR_UNSUPPORTED, "rows_per_cta * ld = %lld exceeds the 31-bit element offset of a CTA",
+                (long long)rows * (long long)d.ld);
+  }
   const int64_t n_chunks = ceil_div(d.n_cells, rows);
   if (n_chunks > 65535 || n_tiles > 65535) {
     delete f;

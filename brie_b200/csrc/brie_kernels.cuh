@@ -297,9 +297,6 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 #pragma unroll
     for (int j = 0; j < EPL; ++j) act |= (a.active[(int64_t)m * a.ld + g0 + j] != 0 ? 1u : 0u) << j;
   }
-  if (!__syncthreads_or(act != 0)) return;
-  const bool all_act = act == (1u << EPL) - 1u;
-
   extern __shared__ __align__(128) float smem[];
   float* s_ring = smem + warp * (kRingStages * kRingArrays * TC);
   uint32_t* q = reinterpret_cast<uint32_t*>(smem + kWarps * kRingStages * kRingArrays * TC +
@@ -322,51 +319,8 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
                         step_n_consts(KC, KG, CELL, LOSS)) * TC +
                 warp * (kRingStages * kRowConstSlots);
 
-  const int64_t row_begin = (int64_t)chunk * a.rows_per_cta;
-  const int64_t row_end = min(row_begin + (int64_t)a.rows_per_cta, a.Nc);
-  const int64_t plane = a.Nc * a.ld;
-  const int64_t mplane = (int64_t)a.M * plane;
-  const bool has_c3 = a.c[2] != nullptr;
-
-  // ring producer: this lane's EPL-float column of each array, one commit group per row
-  const uint32_t ring_lane = (uint32_t)__cvta_generic_to_shared(s_ring) + lane * (EPL * 4);
-  // Lanes whose events are all frozen (converged reference batches) copy nothing: their ring slots are
-  // zero-filled, they compute on zeros and store nothing, so a partly active tile only pays for the
-  // 32-byte sectors that hold active events.
-  const uint32_t rc_lane = (uint32_t)__cvta_generic_to_shared(s_rc) + lane * 4;
-  auto issue_row = [&](int64_t row, int stage) {
-    const bool ok = act != 0 && row < row_end;
-    const int64_t off = ok ? row * a.ld + g0 : 0;
-    const int64_t moff = ok ? (int64_t)m * plane + off : 0;
-    const int64_t coff = ok ? (int64_t)m * a.c_mstride + off : 0;
-    const uint32_t dst = ring_lane + stage * (kRingArrays * TC * 4);
-    cp_async_lane<EPL * 4>(dst + 0 * TC * 4, a.Zl + moff, ok);
-    cp_async_lane<EPL * 4>(dst + 1 * TC * 4, a.Zs + moff, ok);
-    cp_async_lane<EPL * 4>(dst + 2 * TC * 4, a.c[0] + coff, ok);
-    cp_async_lane<EPL * 4>(dst + 3 * TC * 4, a.c[1] + coff, ok);
-    cp_async_lane<EPL * 4>(dst + 4 * TC * 4, has_c3 ? a.c[2] + coff : a.c[0], ok && has_c3);
-    cp_async_lane<EPL * 4>(dst + 5 * TC * 4, a.aZ + moff, ok);
-    cp_async_lane<EPL * 4>(dst + 6 * TC * 4, a.aZ + mplane + moff, ok);
-    cp_async_lane<EPL * 4>(dst + 7 * TC * 4, a.aZ + 2 * mplane + moff, ok);
-    cp_async_lane<EPL * 4>(dst + 8 * TC * 4, a.aZ + 3 * mplane + moff, ok);
-    if (NRC > 0) {
-      // The row's warp-uniform constants ride in the same commit group, one float per lane.  (As plain
-      // loads issued a row ahead they shared a scoreboard with the tile constants loaded before the loop,
-      // and the first use of those waited for the prefetch every row: 23 % of the stall samples.)
-      const bool okc = lane < NRC && row < row_end;
-      const int64_t mr = (int64_t)m * a.Nc + (okc ? row : 0);
-      const float* src = a.Xc;
-      if (lane < KC) src = a.Xc + mr * KC + lane;
-      else if (lane < KC + KG) src = a.Wg + mr * KG + (lane - KC);
-      else if (CELL && lane == KC + KG) src = a.b + mr;
-      else if (CELL) src = a.tau + mr;
-      cp_async_lane<4>(rc_lane + stage * (kRowConstSlots * 4), src, okc);
-    }
-    cp_async_commit();
-  };
-  issue_row(row_begin + warp, 0);
-
-  // per-event constants
+  // Per-event constants of the tile go to shared memory before the barrier that decides whether the tile has
+  // any active event: their loads overlap the `active` loads and that barrier also publishes them.
   if (threadIdx.x < TC) {
     const int64_t g = thread_col();
     s_ev[threadIdx.x] = (a.ev_ids != nullptr && g < a.ld) ? (uint32_t)a.ev_ids[(int64_t)m * a.ld + g]
@@ -395,6 +349,69 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       }
     }
   }
+  if (!__syncthreads_or(act != 0)) return;
+  const bool all_act = act == (1u << EPL) - 1u;
+
+  const int64_t row_begin = (int64_t)chunk * a.rows_per_cta;
+  const int n_rows = (int)(min(row_begin + (int64_t)a.rows_per_cta, a.Nc) - row_begin);
+  const bool has_c3 = a.c[2] != nullptr;
+  // Addresses = one warp-uniform 64-bit base per array (this model's plane at the CTA's first row: blockIdx and
+  // kernel parameters only, so it lives in uniform registers) + a per-lane 32-bit element offset
+  // (local row) * ld + column, which brie_fit_create keeps below 2^31 -- one wide multiply-add per access
+  // instead of a 64-bit multiply-add chain per array and row.
+  const int64_t plane = a.Nc * a.ld;
+  const int64_t mplane = (int64_t)a.M * plane;
+  const int64_t cta_off = (int64_t)m * plane + row_begin * a.ld;
+  float* const bZl = a.Zl + cta_off;
+  float* const bZs = a.Zs + cta_off;
+  float* const bA0 = a.aZ + cta_off;
+  float* const bA1 = a.aZ + mplane + cta_off;
+  float* const bA2 = a.aZ + 2 * mplane + cta_off;
+  float* const bA3 = a.aZ + 3 * mplane + cta_off;
+  const int64_t cnt_off = (int64_t)m * a.c_mstride + row_begin * a.ld;
+  const float* const bC0 = a.c[0] + cnt_off;
+  const float* const bC1 = a.c[1] + cnt_off;
+  const float* const bC2 = has_c3 ? a.c[2] + cnt_off : a.c[0];
+  const int64_t cell0 = (int64_t)m * a.Nc + row_begin;            // first cell of the CTA in the (M, Nc, .) row constants
+  const uint32_t ld32 = (uint32_t)a.ld;
+  const uint32_t col32 = in_ld ? (uint32_t)g0 : 0u;
+
+  // ring producer: this lane's EPL-float column of each array, one commit group per row
+  const uint32_t ring_lane = (uint32_t)__cvta_generic_to_shared(s_ring) + lane * (EPL * 4);
+  // Lanes whose events are all frozen (converged reference batches) copy nothing: their ring slots are
+  // zero-filled, they compute on zeros and store nothing, so a partly active tile only pays for the
+  // 32-byte sectors that hold active events.
+  const uint32_t rc_lane = (uint32_t)__cvta_generic_to_shared(s_rc) + lane * 4;
+  auto issue_row = [&](int lr, int stage) {       // lr: row index within the CTA
+    const bool ok = act != 0 && lr < n_rows;
+    const uint32_t rel = ok ? (uint32_t)lr * ld32 + col32 : 0u;
+    const uint32_t dst = ring_lane + stage * (kRingArrays * TC * 4);
+    cp_async_lane<EPL * 4>(dst + 0 * TC * 4, bZl + rel, ok);
+    cp_async_lane<EPL * 4>(dst + 1 * TC * 4, bZs + rel, ok);
+    cp_async_lane<EPL * 4>(dst + 2 * TC * 4, bC0 + rel, ok);
+    cp_async_lane<EPL * 4>(dst + 3 * TC * 4, bC1 + rel, ok);
+    cp_async_lane<EPL * 4>(dst + 4 * TC * 4, bC2 + (has_c3 ? rel : 0u), ok && has_c3);
+    cp_async_lane<EPL * 4>(dst + 5 * TC * 4, bA0 + rel, ok);
+    cp_async_lane<EPL * 4>(dst + 6 * TC * 4, bA1 + rel, ok);
+    cp_async_lane<EPL * 4>(dst + 7 * TC * 4, bA2 + rel, ok);
+    cp_async_lane<EPL * 4>(dst + 8 * TC * 4, bA3 + rel, ok);
+    if (NRC > 0) {
+      // The row's warp-uniform constants ride in the same commit group, one float per lane.  (As plain
+      // loads issued a row ahead they shared a scoreboard with the tile constants loaded before the loop,
+      // and the first use of those waited for the prefetch every row: 23 % of the stall samples.)
+      const bool okc = lane < NRC && lr < n_rows;
+      const uint32_t r = okc ? (uint32_t)lr : 0u;
+      const float* src = a.Xc;
+      if (lane < KC) src = a.Xc + cell0 * KC + (r * KC + lane);
+      else if (lane < KC + KG) src = a.Wg + cell0 * KG + (r * KG + (lane - KC));
+      else if (CELL && lane == KC + KG) src = a.b + cell0 + r;
+      else if (CELL) src = a.tau + cell0 + r;
+      cp_async_lane<4>(rc_lane + stage * (kRowConstSlots * 4), src, okc);
+    }
+    cp_async_commit();
+  };
+  issue_row(warp, 0);
+
   float wc[KC > 0 ? KC : 1][EPL];
   float xg[KG > 0 ? KG : 1][EPL];
   float bb[EPL], tau[EPL], is2[EPL];
@@ -426,7 +443,6 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       for (int j = 0; j < EPL; ++j) is2[j] = fast_exp(-2.0f * tau[j]);
     }
   }
-  __syncthreads();  // s_L, s_k visible
 
   float acc[NEV > 0 ? NEV : 1][EPL];
 #pragma unroll
@@ -438,8 +454,9 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   const uint32_t lt_mask = (1u << lane) - 1u;
 
   int stage = 0;
-  for (int64_t row = row_begin + warp; row < row_end; row += kWarps, stage ^= 1) {
-    issue_row(row + kWarps, stage ^ 1);   // prefetch the next row (zero-size copies past the end)
+  for (int lr = warp; lr < n_rows; lr += kWarps, stage ^= 1) {
+    const int64_t row = row_begin + lr;
+    issue_row(lr + kWarps, stage ^ 1);    // prefetch the next row (zero-size copies past the end)
     cp_async_wait<1>();                   // this row's group has landed
     float xc[KC > 0 ? KC : 1], wg[KG > 0 ? KG : 1];
     float b_row = 0.f, tau_row = 0.f;
@@ -596,13 +613,13 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
           }
         }
       }
-      const int64_t moff = (int64_t)m * plane + row * a.ld + g0;
-      __stcs(reinterpret_cast<Vec*>(a.Zl + moff), vec_make<EPL>(mu));
-      __stcs(reinterpret_cast<Vec*>(a.Zs + moff), vec_make<EPL>(lam));
-      __stcs(reinterpret_cast<Vec*>(a.aZ + moff), vec_make<EPL>(m1));
-      __stcs(reinterpret_cast<Vec*>(a.aZ + mplane + moff), vec_make<EPL>(v1));
-      __stcs(reinterpret_cast<Vec*>(a.aZ + 2 * mplane + moff), vec_make<EPL>(m2));
-      __stcs(reinterpret_cast<Vec*>(a.aZ + 3 * mplane + moff), vec_make<EPL>(v2));
+      const uint32_t rel = (uint32_t)lr * ld32 + col32;
+      __stcs(reinterpret_cast<Vec*>(bZl + rel), vec_make<EPL>(mu));
+      __stcs(reinterpret_cast<Vec*>(bZs + rel), vec_make<EPL>(lam));
+      __stcs(reinterpret_cast<Vec*>(bA0 + rel), vec_make<EPL>(m1));
+      __stcs(reinterpret_cast<Vec*>(bA1 + rel), vec_make<EPL>(v1));
+      __stcs(reinterpret_cast<Vec*>(bA2 + rel), vec_make<EPL>(m2));
+      __stcs(reinterpret_cast<Vec*>(bA3 + rel), vec_make<EPL>(v2));
     }
     if (NCELL > 0) {
       float* pc = a.part_cell + (((int64_t)tile * a.M + m) * a.Nc + row) * NCELL;
