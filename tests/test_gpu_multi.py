@@ -77,8 +77,10 @@ def test_sharded_fitBRIE_matches_single_gpu(tmp_path):
         d = np.abs(b1[k] - b2[k])
         # Psi is pinned by the data; the gene-feature weights are only weakly identified (150 events
         # per cell), so Adam's sign-like steps let them drift by ~lr between summation orders
-        tol_med = 1e-5 if k == 'Psi' else 2e-3
-        assert np.median(d) < tol_med and np.quantile(d, 0.99) < 1e-2 and d.max() < 5e-2, k
+        # (measured after the per-cell butterfly reduction changed the order once more: Psi median 6e-6 / max 3e-3,
+        # gene_coeff 4e-4 / 1.5e-3, intercept 1.8e-3 / 2.1e-3, sigma 1e-5 / 5e-4, cell_coeff 2.1e-3 / 1.3e-2)
+        tol_med = 1e-5 if k == 'Psi' else 5e-3
+        assert np.median(d) < tol_med and np.quantile(d, 0.99) < 2e-2 and d.max() < 5e-2, k
     assert np.abs(b1['lg'] - b2['lg']).max() <= 1e-3 * np.abs(b1['lg']).max()
 
 
