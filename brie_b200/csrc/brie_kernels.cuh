@@ -221,16 +221,20 @@ __device__ __forceinline__ void cp_async_lane(uint32_t dst_smem, const void* src
 // Each warp walks its rows of one (32 x EPL)-event segment through a private two-stage
 // shared-memory ring filled with cp.async (EPL floats per lane per array, 9 arrays =
 // 4.6 KB per row at EPL = 4): the next row streams in from HBM while the current one is
-// processed, so loads in flight do not depend on register-resident state.  A lane
-// reads back exactly the bytes it copied, so the ring needs no barrier.
+// processed, so loads in flight do not depend on register-resident state.  The row's
+// warp-uniform constants (Xc[c, :], Wg[c, :], per-cell intercept / sigma_log) ride in the
+// same commit group, one float per lane; one __syncwarp after the wait makes the stage
+// readable by every lane of the warp (no CTA barrier in the row loop).
 // One row is processed in three phases:
 //   A (dense, lane = EPL events): KL terms and gradients, shared-parameter
-//     accumulators; elements with reads (n > 0) are pushed, compacted by ballot/popc
-//     prefix, into the warp's shared-memory work queue;
-//   B (compacted): lanes take queue items round-robin and run the S Monte-Carlo
-//     samples (Philox + Box-Muller + likelihood gradient) -- zero-count elements,
-//     80-87 % of real data, cost nothing here and the lanes stay converged;
-//   C (dense): owners read their MC sums back, Adam-update and store (16 B stores at EPL = 4).
+//     accumulators; elements with reads (n > 0) push their tile column, compacted by
+//     ballot/popc prefix, into the warp's shared-memory work queue;
+//   B (compacted): lanes take queue items round-robin, read the element from the ring
+//     stage, run the S Monte-Carlo samples (Philox + Box-Muller + likelihood gradient)
+//     and leave the sums in the element's count slots -- zero-count elements, 80-87 % of
+//     real data, cost nothing here and the lanes stay converged;
+//   C (dense): owners subtract their slots (zeros where there were no reads),
+//     Adam-update and store (16 B stores at EPL = 4).
 constexpr int kQueueFields = 1;   // tile column of the element; its data is read from, and its results written to, the row's ring slots
 constexpr int kRingArrays = 9;    // Z_loc, Z_std_log, c1, c2, c3, m_loc, v_loc, m_std, v_std
 constexpr int kRingStages = 2;

@@ -33,6 +33,25 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+def gathered_round_is_cheaper(cols, n_events, n_cells, n_layers, n_steps):
+    """Extension round on gathered sub-fits or in place?  cols[m]: local event indices still active in model m.
+
+    Bytes per cell and step.  In place, every 8-event block (one 32-byte sector of each float32 array) that
+    holds an active event moves whole: 48 B of state per model, and the counts once for the models
+    co-resident on the tile.  Gathered, only active events move, but each model reads its own copy of the
+    counts; add the gather and scatter passes (about 3 step-equivalents) and ~15 ms of set-up per round,
+    expressed in the same unit.  Gathered must win by 10 % to be chosen."""
+    M = len(cols)
+    n_act = sum(len(c) for c in cols)
+    ev = np.zeros((M, _round_up(max(n_events, 1), 8)), bool)
+    for m in range(M):
+        ev[m, cols[m]] = True
+    blk = ev.reshape(M, -1, 8).any(axis=2)
+    in_place = 8.0 * (48 * blk.sum() + 4 * n_layers * blk.any(axis=0).sum())
+    gathered = n_act * (48 + 4 * n_layers) * (1.0 + 3.0 / max(n_steps, 1)) + 1e11 / max(n_cells * n_steps, 1)
+    return gathered <= 0.9 * in_place
+
+
 class FitEngine:
     """Device-resident batched fit.
 
@@ -329,19 +348,8 @@ class FitEngine:
         n_act = sum(len(c) for c in cols)
         if n_act == 0 or n_act == M * self.Ng:
             return False
-        if not force:
-            # bytes per cell and step: in place, every 8-event block with an active event moves whole
-            # (48 B state per model, 12 B counts shared by the models co-resident on the tile);
-            # gathered, only active events move but each model reads its own counts; plus the
-            # gather / scatter passes and ~15 ms of set-up per round
-            ev = np.zeros((M, _round_up(self.Ng, 8)), bool)
-            for m in range(M):
-                ev[m, cols[m]] = True
-            blk = ev.reshape(M, -1, 8).any(axis=2)
-            in_place = 8.0 * (48 * blk.sum() + 4 * L * blk.any(axis=0).sum())
-            gathered = n_act * (48 + 4 * L) * (1.0 + 3.0 / max(n_steps, 1)) + 1e11 / max(Nc * n_steps, 1)
-            if gathered > 0.9 * in_place:
-                return False
+        if not force and not gathered_round_is_cheaper(cols, self.Ng, Nc, L, n_steps):
+            return False
         per_col = M * Nc * (L + 6) * 4 * 1.05 + M * (n_steps + 64) * 4
         max_ld = int(0.8 * self._free_bytes() / per_col) // 32 * 32
         nmax = max(len(c) for c in cols)

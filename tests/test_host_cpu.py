@@ -310,3 +310,26 @@ def test_dump_results_header_matches_published_table():
     line = df.to_csv(sep='\t', float_format='%.3e').splitlines()[1].split('\t')
     assert len(line) == 10 and all('e' in v for v in line[3:])       # quant.py:129-130 format
     assert np.allclose(df['cdr'].values, (X > 0).mean(0))
+
+
+def test_gathered_vs_in_place_cost_model():
+    """Which form an extension round takes (engine.gathered_round_is_cheaper): --batchSize 500000 batches are
+    100 events at 5k cells (whole 8-event blocks: in place, counts shared by the models), 5 events at 100k
+    cells and 1 event at 1M cells (finer than a 32-byte sector: gathered), whatever fraction is still active."""
+    from brie_b200.engine import gathered_round_is_cheaper
+
+    def cols(Ng, M, group, p, seed=0):
+        act = np.random.default_rng(seed).random((M, -(-Ng // group))) < p
+        g = np.arange(Ng) // group
+        return [np.flatnonzero(act[m, g]) for m in range(M)]
+
+    for p in (0.6, 0.3, 0.1, 0.03):
+        assert not gathered_round_is_cheaper(cols(5000, 2, 100, p), 5000, 5000, 3, 500)          # C2
+        assert gathered_round_is_cheaper(cols(2500, 4, 5, p), 2500, 100000, 3, 500)              # C3 share
+        assert gathered_round_is_cheaper(cols(1250, 2, 1, p), 1250, 1000000, 3, 500)             # C5 share
+    # tiny problems: the fixed set-up cost of a gathered round dominates
+    assert not gathered_round_is_cheaper(cols(64, 1, 1, 0.3), 64, 50, 3, 500)
+    # nothing active in one model, a few batches in the other
+    c = cols(2500, 2, 5, 0.1)
+    c[0] = c[0][:0]
+    assert gathered_round_is_cheaper(c, 2500, 100000, 3, 500)
