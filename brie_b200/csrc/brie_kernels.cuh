@@ -125,6 +125,48 @@ __device__ __forceinline__ void adam_update(float& x, float& m, float& v, float 
   x -= (m * alpha) * rcp_approx(sqrt_approx(v) + kAdamEps);
 }
 
+// Packed FP32 pairs (sm_100a FFMA2 / FADD2 / FMUL2: one issue slot, two IEEE-rounded results).  Experimental path
+// of the dense phases of the step kernel, compiled in with -DBRIE_F32X2=1 (default off until A/B-ed on hardware).
+#ifndef BRIE_F32X2
+#define BRIE_F32X2 0
+#endif
+#define BRIE_F2_BINARY(name, ptx)                                                                          \
+  __device__ __forceinline__ float2 name(float2 a, float2 b) {                                             \
+    float2 d;                                                                                              \
+    asm("{.reg .b64 ra, rb, rd;\n\t mov.b64 ra, {%2, %3};\n\t mov.b64 rb, {%4, %5};\n\t" ptx               \
+        " rd, ra, rb;\n\t mov.b64 {%0, %1}, rd;}"                                                          \
+        : "=f"(d.x), "=f"(d.y)                                                                             \
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                         \
+    return d;                                                                                              \
+  }
+BRIE_F2_BINARY(f2_add, "add.rn.f32x2")
+BRIE_F2_BINARY(f2_sub, "sub.rn.f32x2")
+BRIE_F2_BINARY(f2_mul, "mul.rn.f32x2")
+#undef BRIE_F2_BINARY
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd;\n\t mov.b64 ra, {%2, %3};\n\t mov.b64 rb, {%4, %5};\n\t mov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\t mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 f2_splat(float x) { return make_float2(x, x); }
+
+// adam_update on a pair.  (g^2 - v is a multiply and a subtract here, not one fused multiply-add: there is no
+// packed form with a negated addend; the difference is one rounding of g^2.)
+__device__ __forceinline__ void adam_update2(float& x0, float& x1, float& m0, float& m1, float& v0, float& v1,
+                                             float g0, float g1, float alpha) {
+  const float2 g = make_float2(g0, g1);
+  float2 m = make_float2(m0, m1), v = make_float2(v0, v1);
+  m = f2_fma(f2_sub(g, m), f2_splat(kB1c), m);
+  v = f2_fma(f2_sub(f2_mul(g, g), v), f2_splat(kB2c), v);
+  const float2 den = f2_add(make_float2(sqrt_approx(v.x), sqrt_approx(v.y)), f2_splat(kAdamEps));
+  const float2 step = f2_mul(f2_mul(m, f2_splat(alpha)), make_float2(rcp_approx(den.x), rcp_approx(den.y)));
+  const float2 x = f2_sub(make_float2(x0, x1), step);
+  x0 = x.x; x1 = x.y; m0 = m.x; m1 = m.y; v0 = v.x; v1 = v.y;
+}
+
 __device__ __forceinline__ float clip9(float x) { return fminf(fmaxf(x, -9.0f), 9.0f); }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -502,6 +544,64 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     }
     float gmu[EPL], glam[EPL];
     uint32_t nz = 0;
+#if BRIE_F32X2
+    static_assert(EPL % 2 == 0, "packed pairs need an even number of events per lane");
+    float2 cacc2[NCELL > 0 ? NCELL : 1];
+#pragma unroll
+    for (int i = 0; i < (NCELL > 0 ? NCELL : 1); ++i) cacc2[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int p = 0; p < EPL / 2; ++p) {
+      const int j0 = 2 * p, j1 = 2 * p + 1;
+      const float2 tj = CELL ? f2_splat(tau_row) : make_float2(tau[j0], tau[j1]);
+      const float2 i2 = CELL ? f2_splat(is2_row) : make_float2(is2[j0], is2[j1]);
+      float2 pm = CELL ? f2_splat(b_row) : make_float2(bb[j0], bb[j1]);
+#pragma unroll
+      for (int k = 0; k < KC; ++k) pm = f2_fma(f2_splat(xc[k]), make_float2(wc[k][j0], wc[k][j1]), pm);
+#pragma unroll
+      for (int k = 0; k < KG; ++k) pm = f2_fma(f2_splat(wg[k]), make_float2(xg[k][j0], xg[k][j1]), pm);
+      const float2 d = f2_sub(make_float2(lam[j0], lam[j1]), tj);
+      const float2 dd = f2_mul(d, f2_splat(2.0f * kLog2e));
+      const float2 e2 = make_float2(ex2_approx(dd.x), ex2_approx(dd.y));   // s^2 / sigma^2
+      const float2 diff = f2_sub(make_float2(mu[j0], mu[j1]), pm);
+      const float2 r = f2_mul(diff, i2);                                   // (mu - m) / sigma^2
+      const float2 q2 = f2_mul(diff, r);                                   // ((mu - m) / sigma)^2
+      const float2 nr = make_float2(-r.x, -r.y);
+      const float2 e2m1 = f2_add(e2, f2_splat(-1.0f));
+      gmu[j0] = r.x; gmu[j1] = r.y;
+      glam[j0] = e2m1.x; glam[j1] = e2m1.y;
+      if (c1[j0] + c2[j0] + c3[j0] > 0.f) nz |= 1u << j0;
+      if (c1[j1] + c2[j1] + c3[j1] > 0.f) nz |= 1u << j1;
+      const float2 gt = f2_sub(f2_sub(f2_splat(1.0f), q2), e2);            // d loss / d sigma_log
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        const float2 t = f2_fma(f2_splat(xc[k]), nr, make_float2(acc[k][j0], acc[k][j1]));
+        acc[k][j0] = t.x; acc[k][j1] = t.y;
+      }
+      if (!CELL) {
+        const float2 t = f2_sub(make_float2(acc[T::kGB][j0], acc[T::kGB][j1]), r);
+        acc[T::kGB][j0] = t.x; acc[T::kGB][j1] = t.y;
+        const float2 u = f2_add(make_float2(acc[T::kGT][j0], acc[T::kGT][j1]), gt);
+        acc[T::kGT][j0] = u.x; acc[T::kGT][j1] = u.y;
+      }
+      if (LOSS) {                                                          // TFP _kl_normal_normal
+        const float2 kl = f2_sub(f2_fma(f2_splat(0.5f), q2, f2_mul(f2_splat(0.5f), e2m1)), d);
+        const float2 t = f2_add(make_float2(acc[T::kLoss][j0], acc[T::kLoss][j1]), kl);
+        acc[T::kLoss][j0] = t.x; acc[T::kLoss][j1] = t.y;
+      }
+      if (NCELL > 0) {
+        const float2 nrm = make_float2((g0 + j0) < a.Ng ? nr.x : 0.f, (g0 + j1) < a.Ng ? nr.y : 0.f);
+#pragma unroll
+        for (int k = 0; k < KG; ++k) cacc2[k] = f2_fma(make_float2(xg[k][j0], xg[k][j1]), nrm, cacc2[k]);
+        if (CELL) {
+          const float2 gm = make_float2((g0 + j0) < a.Ng ? gt.x : 0.f, (g0 + j1) < a.Ng ? gt.y : 0.f);
+          cacc2[KG] = f2_add(cacc2[KG], nrm);
+          cacc2[KG + 1] = f2_add(cacc2[KG + 1], gm);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NCELL; ++i) cacc[i] = cacc2[i].x + cacc2[i].y;
+#else
 #pragma unroll
     for (int j = 0; j < EPL; ++j) {
       const float tj = CELL ? tau_row : tau[j];
@@ -536,6 +636,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
         }
       }
     }
+#endif
 
     // ---- phase B: compacted Monte-Carlo work ----
     uint32_t bal[EPL];
@@ -601,12 +702,23 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       vec_get<EPL>(st[7 * 32], m2);
       vec_get<EPL>(st[8 * 32], v2);
       if (all_act) {
+#if BRIE_F32X2
+#pragma unroll
+        for (int p = 0; p < EPL / 2; ++p) {
+          const int j0 = 2 * p, j1 = 2 * p + 1;
+          adam_update2(mu[j0], mu[j1], m1[j0], m1[j1], v1[j0], v1[j1], gmu[j0], gmu[j1], a.alpha);
+          adam_update2(lam[j0], lam[j1], m2[j0], m2[j1], v2[j0], v2[j1], glam[j0], glam[j1], a.alpha);
+          mu[j0] = clip9(mu[j0]);  // Variable constraint (model_TFProb.py:80-81)
+          mu[j1] = clip9(mu[j1]);
+        }
+#else
 #pragma unroll
         for (int j = 0; j < EPL; ++j) {
           adam_update(mu[j], m1[j], v1[j], gmu[j], a.alpha);
           adam_update(lam[j], m2[j], v2[j], glam[j], a.alpha);
           mu[j] = clip9(mu[j]);  // Variable constraint (model_TFProb.py:80-81)
         }
+#endif
       } else {
 #pragma unroll
         for (int j = 0; j < EPL; ++j) {
