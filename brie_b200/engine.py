@@ -134,6 +134,10 @@ class FitEngine:
             return t
 
         self.counts = [padded(c) for c in counts]
+        # read counts are non-negative; the step kernel relies on it (an element whose counts sum to zero has
+        # zeros in every layer, brie_kernels.cuh phase B)
+        if min(float(c.min()) for c in self.counts) < 0:
+            raise ValueError("brie_b200: count layers must be non-negative")
         self.h2d_bytes = sum(int(np.prod(c.shape)) * 4 for c in counts)
         if effLen is not None:
             eff = np.ones((3, ld), np.float32)

@@ -11,6 +11,7 @@
  *  - Every (cells, events) matrix is row-major with leading dimension `ld`
  *    floats (ld % 4 == 0, ld >= n_events); columns >= n_events are padding and
  *    must hold zero counts.  Same layout as the reference's (Nc, Ng) tensors.
+ *    Counts are non-negative (read counts plus the pseudo-count); the step kernel relies on it.
  *  - `n_models` independent models (the full/base fit plus the LRT refits of
  *    model_wrap.py:155-187) are batched in every launch; model-major arrays are
  *    (n_models, ...).  Every model has its own design matrix Xc[model] (Nc, Kc):
