@@ -223,7 +223,7 @@ def main():
     value = world * units_per_step * K / (ms * 1e-3)
 
     # roofline of the fused step kernel: algorithmic bytes = 12 B counts (shared by the M models)
-    # + 48 B state per model per cell x event
+    # + 48 B state traffic (24 B read + 24 B written) per model per cell x event
     peak, peak_src = hbm_peak()
     alg_bytes = NC * NG * (12 + 48 * M)
     k_ms = kms / max(kn, 1)
@@ -285,7 +285,7 @@ def main():
                "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic",
                "config": {"workload": WORKLOAD, "cells": NC, "events_per_gpu": NG, "models": M, "mc_size": S,
-                          "nonzero_fraction": nnz_frac, "l2": "state 2.7 GB per GPU >> 126 MB L2 (inputs larger than L2)",
+                          "nonzero_fraction": nnz_frac, "l2": "1.5 GB resident per GPU (0.3 GB counts + 1.2 GB state), 2.7 GB moved per step >> 126 MB L2 (inputs larger than L2)",
                           "parallelism": "events sharded x%d, no collective" % world},
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
                "cpu_baseline": cpu, "fit_lrt_wall_s": fit_wall}
