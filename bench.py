@@ -146,7 +146,8 @@ def run_reference_arm(args):
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": WORKLOAD, "note": "restated reference (PyTorch-CPU eager, not TensorFlow: TF/TFP "
                       "are not installable here); one step = fwd+bwd+Adam of ONE model over a bounded sample: " + sample},
-           "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                            "value_at_nproc_6": cpu_reference_run(min(n, 20), 2, min(6, threads))[0]},
            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -277,8 +278,9 @@ def main():
     if rank == 0 and not args.no_cpu:
         threads = os.cpu_count() or 1
         v, cms, sample = cpu_reference_run(40, 3, threads)
+        v6, _, _ = cpu_reference_run(20, 2, min(6, threads))      # the reference's own default, --nproc 6 (quant.py:183)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample, "ms_per_step": cms,
-               "note": "restated reference, PyTorch-CPU eager -- not TensorFlow"}
+               "value_at_nproc_6": v6, "note": "restated reference, PyTorch-CPU eager -- not TensorFlow"}
 
     if rank == 0:
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
