@@ -192,9 +192,46 @@ __device__ __forceinline__ void mc_samples(float mu, float s, float c1, float c2
   for (int s0 = 0; s0 < S; s0 += 4) {
     float eps[4];
     brie_normals4(event, cell, step, stream0 + (uint32_t)(s0 >> 2), seed, eps);
+#if BRIE_F32X2
+    // two samples per instruction where both exist (S = 3: samples 0 and 1 as a pair, sample 2 alone)
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+      if (s0 + j + 1 < S) {
+        const float2 ep = make_float2(eps[j], eps[j + 1]);
+        const float2 z = f2_fma(f2_splat(s), ep, f2_splat(mu));
+        const float2 az = make_float2(fabsf(z.x), fabsf(z.y));
+        const float2 ea = f2_mul(az, f2_splat(-kLog2e));
+        const float2 e = make_float2(ex2_approx(ea.x), ex2_approx(ea.y));          // exp(-|z|)
+        const float2 ope = f2_add(e, f2_splat(1.0f));
+        const float2 inv = make_float2(rcp_approx(ope.x), rcp_approx(ope.y));
+        const float2 lo = f2_mul(e, inv);
+        const float2 psi = make_float2(z.x >= 0.f ? inv.x : lo.x, z.y >= 0.f ? inv.y : lo.y);
+        const float2 q = make_float2(z.x >= 0.f ? lo.x : inv.x, z.y >= 0.f ? lo.y : inv.y);
+        const float2 D = f2_fma(psi, f2_splat(L1), f2_fma(q, f2_splat(L2), f2_splat(L3)));
+        const float2 rD = make_float2(rcp_approx(D.x), rcp_approx(D.y));
+        const float2 t1 = f2_fma(f2_splat(c1), q, f2_mul(f2_splat(-c2), psi));
+        const float2 t2 = f2_mul(f2_mul(f2_splat(ndL), f2_mul(psi, q)), rD);
+        const float2 g = f2_sub(t1, t2);
+        gsum += g.x;
+        gsum += g.y;
+        gesum = fmaf(g.x, ep.x, gesum);
+        gesum = fmaf(g.y, ep.y, gesum);
+        if (LOSS) {
+          const float2 lsp = make_float2(fminf(z.x, 0.f) - fast_log(ope.x), fminf(z.y, 0.f) - fast_log(ope.y));
+          const float2 u = f2_fma(f2_splat(c1), lsp, f2_mul(f2_splat(c2), f2_sub(lsp, z)));
+          llsum += u.x - n * fast_log(D.x);
+          llsum += u.y - n * fast_log(D.y);
+        }
+      }
+    }
+#endif
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+#if BRIE_F32X2
+      if (s0 + j < S && !(s0 + (j | 1) < S)) {   // the unpaired last sample
+#else
       if (s0 + j < S) {
+#endif
         const float z = fmaf(s, eps[j], mu);
         const float e = ex2_approx(-kLog2e * fabsf(z));      // exp(-|z|)
         const float inv = rcp_approx(1.0f + e);
