@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 BRIE_MAX_MODELS = 32
-ABI_VERSION = 4
+ABI_VERSION = 5
 TARGETS = {"ELBO": 0, "marginLik": 1}
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("BRIE_LIB_PATH", os.path.join(_HERE, "libbrie_b200.so"))
@@ -64,6 +64,14 @@ SYMBOLS = {
     "brie_fit_set_active_blocks": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int32)]),
     "brie_fit_step_phase": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
     "brie_fit_cell_grad": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_int64)]),
+    "brie_comm_nccl_version": (C.c_int, []),
+    "brie_comm_unique_id": (C.c_int, [_P]),
+    "brie_comm_create": (C.c_int, [_P, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "brie_comm_destroy": (C.c_int, [_P]),
+    "brie_comm_allreduce_f32": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "brie_comm_allreduce_f64": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "brie_comm_allreduce_count": (C.c_int64, [_P]),
+    "brie_fit_set_comm": (C.c_int, [_P, _P]),
     "brie_fit_eval_loss_gene": (C.c_int, [_P, C.c_int32, C.c_int32, _P, _P]),
     "brie_fit_posterior": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P]),
     "brie_fit_group_trace": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),

@@ -37,9 +37,16 @@ def quant(in_file, cell_file=None, gene_file=None, out_file=None,
           intercept=None, intercept_mode='gene', nproc=1, min_counts=50,
           min_counts_uniq=10, min_cells_uniq=30, min_MIF_uniq=0.001,
           min_iter=5000, max_iter=20000, MC_size=1, batch_size=500000,
-          pseudo_count=0.01, base_mode='full', seed=0):
+          pseudo_count=0.01, base_mode='full', seed=0, out_dir=None, resume=False):
     """CLI driver (quant.py:13-130).  `nproc` is accepted for compatibility (host threads are
     not on the hot path any more); `seed` keys the counter-based noise (new, default 0).
+    `out_dir` (new): directory for `.npy` memory maps of the dense (cells, events) output layers
+    Psi / Psi_95CI / Z_std, written event chunk by event chunk and rank by rank -- the reference keeps
+    them dense in RAM (model_wrap.py:289-292, "TODO: introduce sparse matrix for this"), 80 GB each at
+    1M x 20k; the output container then references the maps instead of embedding the arrays.  Under
+    torchrun it defaults to `<out_file stem>.layers/`, so no (cells, events) array ever travels through a
+    collective.  `resume` (new, needs out_dir): skip the event chunks a previous run of the same fit left
+    there (checkpoint / restart).
 
     Multi-GPU: launch one process per GPU (`python -m torch.distributed.run --nproc-per-node N
     -m brie_b200.bin.quant ...`); every rank reads the input, fits its own event shard
@@ -49,6 +56,11 @@ def quant(in_file, cell_file=None, gene_file=None, out_file=None,
         print("No given out_file, use the dir for input file.")
         out_file = os.path.dirname(os.path.abspath(in_file)) + "/brie_quant.h5ad"
     os.makedirs(os.path.dirname(os.path.abspath(out_file)), exist_ok=True)
+    if out_dir is None and world > 1:
+        out_dir = ".".join(os.path.abspath(out_file).split('.')[:-1]) + ".layers"
+    if resume and out_dir is None:
+        print("[BRIE2] Error: --resume needs --outDir.")
+        sys.exit(1)
 
     if in_file.endswith(".h5ad"):
         adata = io_utils.read_h5ad(in_file)
@@ -94,7 +106,8 @@ def quant(in_file, cell_file=None, gene_file=None, out_file=None,
     fitBRIE(adata, Xc=Xc, Xg=Xg, LRT_index=LRT_index, layer_keys=layer_keys,
             intercept=intercept, intercept_mode=intercept_mode,
             min_iter=min_iter, max_iter=max_iter, MC_size=MC_size, batch_size=batch_size,
-            pseudo_count=pseudo_count, base_mode=base_mode, tau_prior=tau_prior, seed=seed)
+            pseudo_count=pseudo_count, base_mode=base_mode, tau_prior=tau_prior, seed=seed,
+            **(dict(out_dir=out_dir, resume=resume) if out_dir is not None else {}))
 
     adata.uns['brie_version'] = brie_b200.__version__
     adata.uns['Xc_ids'] = Xc_ids
@@ -159,8 +172,15 @@ def main():
         help="Number of processes for computing [default: %default]")
     group2.add_option("--seed", type=int, dest="seed", default=0,
         help="Key of the counter-based MC noise and initial values [default: %default]")
+    group3 = OptionGroup(parser, "Large outputs (not in the reference)")
+    group3.add_option("--outDir", dest="out_dir", default=None,
+        help="Directory for .npy memory maps of the dense output layers Psi, Psi_95CI, Z_std (written "
+             "chunk by chunk; the output file references them) [default: in RAM; <out_file>.layers under torchrun]")
+    group3.add_option("--resume", action="store_true", dest="resume", default=False,
+        help="With --outDir: skip the event chunks a previous run of the same fit has finished")
     parser.add_option_group(group1)
     parser.add_option_group(group2)
+    parser.add_option_group(group3)
 
     (options, args) = parser.parse_args()
     if len(sys.argv[1:]) == 0:
@@ -184,7 +204,8 @@ def main():
           intercept, options.intercept_mode, options.nproc, options.min_count,
           options.min_uniq_count, options.min_cell, options.min_MIF,
           options.min_iter, options.max_iter, options.MC_size,
-          options.batch_size, options.pseudo_count, options.test_base, options.seed)
+          options.batch_size, options.pseudo_count, options.test_base, options.seed,
+          options.out_dir, options.resume)
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         import torch.distributed as dist
         if dist.is_initialized():

@@ -10,7 +10,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
-UNITS = ["brie_abi.cu", "brie_ingest.cu"]
+UNITS = ["brie_abi.cu", "brie_ingest.cu", "brie_comm.cu"]
 HEADERS = [os.path.join(_CSRC, h) for h in ("brie_kernels.cuh", "brie_margin.cuh", "brie_philox.h", "brie_host.h")] + \
     [os.path.join(os.path.dirname(_HERE), "include", "brie_b200.h")]
 OBJ_DIR = os.path.join(_HERE, "build")
@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(len(UNITS)) as ex:
         objs = list(ex.map(compile_unit, UNITS))
-    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs, check=True)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-ldl"], check=True)
     return OUT
 
 

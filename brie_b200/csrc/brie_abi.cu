@@ -21,7 +21,10 @@ namespace {
 thread_local std::string g_err;
 }
 
+struct brie_comm;
 namespace brie {
+int comm_allreduce_sum_f32(brie_comm* c, float* buf, int64_t n, cudaStream_t s);   // brie_comm.cu
+
 int fail(int code, const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -55,23 +58,30 @@ struct brie_fit {
   int64_t blk_stride = 0;
   int32_t n_blk[BRIE_MAX_MODELS] = {0};
   int blk_tiles = 0;
+  brie_comm* comm = nullptr;   // event-sharded fit with shared per-cell parameters: G is all-reduced every step
 };
 
 using namespace brie;
 
 namespace {
 
+constexpr int kMaxDevices = 64;
+
 bool kc_supported(int k) { return k == 0 || k == 1 || k == 2 || k == 4 || k == 8 || k == 16; }
 bool kg_supported(int k) { return k == 0 || k == 4 || k == 8; }
 
 template <int KC, int KG, bool CELL, bool LOSS>
 cudaError_t launch_step(const StepArgs& a, dim3 grid, cudaStream_t s) {
-  static bool configured = false;  // per instantiation: opt in to > 48 KB dynamic shared memory
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(elbo_step_kernel<KC, KG, CELL, LOSS>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, step_smem_bytes(KC, KG, CELL, LOSS));
+  // per instantiation and per device: opt in to > 48 KB dynamic shared memory (the attribute is per device)
+  static bool configured[kMaxDevices] = {false};
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
+    e = cudaFuncSetAttribute(elbo_step_kernel<KC, KG, CELL, LOSS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             step_smem_bytes(KC, KG, CELL, LOSS));
     if (e != cudaSuccess) return e;
-    configured = true;
+    if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
   }
   elbo_step_kernel<KC, KG, CELL, LOSS><<<grid, kThreads, step_smem_bytes(KC, KG, CELL, LOSS), s>>>(a);
   return cudaGetLastError();
@@ -391,11 +401,13 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
       g.KC = d.Kc; g.KG = d.Kg; g.cell_mode = d.cell_mode; g.NEV = nev; g.NCELL = f->ncell;
       for (int m = 0; m < M; ++m) g.model_id[m] = d.model_id[m];
       const size_t smem = (size_t)kWarps * nev * kMarginTile * sizeof(float);
-      static bool configured = false;
-      if (!configured) {
+      static bool configured[kMaxDevices] = {false};   // per device, as in launch_step
+      int dev = 0;
+      BRIE_CUDA(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
         BRIE_CUDA(cudaFuncSetAttribute(margin_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        kWarps * (BRIE_MAX_KC + 3) * kMarginTile * (int)sizeof(float)));
-        configured = true;
+        if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
       }
       const dim3 grid(M, cell_tiles, f->sz.n_row_chunks);
       margin_step_kernel<<<grid, kThreads, smem, s>>>(g);
@@ -498,13 +510,25 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
 int brie_fit_run_steps(brie_fit* f, int32_t n_steps, int32_t trace_slot0, void* stream) {
   if (!f || !f->bound) return fail(BRIE_ERR_ARG, "fit not bound");
   if (n_steps < 0) return fail(BRIE_ERR_ARG, "n_steps must be >= 0");
+  const int64_t n_G = (int64_t)f->d.n_models * f->d.n_cells * f->ncell;
   for (int i = 0; i < n_steps; ++i) {
     const int slot = trace_slot0 >= 0 ? trace_slot0 + i : -1;
     int rc = brie_fit_step_phase(f, 0, slot, stream);
     if (rc) return rc;
+    if (f->comm && n_G > 0) {   // the path's one exchange step, in stream order between the two halves
+      rc = comm_allreduce_sum_f32(f->comm, (float*)f->buf.scratch + f->off_G, n_G, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
     rc = brie_fit_step_phase(f, 1, slot, stream);
     if (rc) return rc;
   }
+  return BRIE_OK;
+}
+
+int brie_fit_set_comm(brie_fit* f, brie_comm* comm) {
+  if (!f) return fail(BRIE_ERR_ARG, "null argument");
+  if (f->step_open) return fail(BRIE_ERR_ARG, "a split step is still open");
+  f->comm = comm;
   return BRIE_OK;
 }
 

@@ -199,6 +199,14 @@ class FitEngine:
         b.active, b.loss_trace, b.scratch = self.active.data_ptr(), self.loss_trace.data_ptr(), self.scratch.data_ptr()
         self.bufs = b
         _lib.check(self.lib.brie_fit_bind(h, C.byref(b)))
+        # Shared per-cell parameters on an event shard: the library all-reduces their gradients itself,
+        # in stream order inside brie_fit_run_steps (BRIE_HOST_ALLREDUCE=1 keeps the older per-step
+        # torch.distributed round trip, for A/B only).
+        self._comm = None
+        if dist_group is not None and self.shared and not os.environ.get("BRIE_HOST_ALLREDUCE"):
+            from . import comm
+            self._comm = comm.get(dist_group)
+            _lib.check(self.lib.brie_fit_set_comm(h, self._comm.h))
         self.n_iter = None
         self.losses = None
         self.loss_gene = None
@@ -272,7 +280,7 @@ class FitEngine:
 
     def run_steps(self, n, trace_slot0=-1):
         with torch.cuda.device(self.device):
-            if self.dist_group is None or not self.shared:
+            if self.dist_group is None or not self.shared or self._comm is not None:
                 _lib.check(self.lib.brie_fit_run_steps(self.h, int(n), int(trace_slot0), self._stream()))
                 return
             import torch.distributed as dist
@@ -292,7 +300,10 @@ class FitEngine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.brie_fit_group_trace(self.h, int(n_slots), self.group_size, self.n_groups,
                                                      out.data_ptr(), self._stream()))
-        if self.dist_group is not None and self.shared:
+        # A fit handed a process group spans the ranks with ONE convergence group (fit_BRIE_matrix passes
+        # dist_group only for the un-batched branch, model_wrap.py:261-269): its stop rule needs the loss
+        # summed over every rank's events -- also for the per-event (gene-mode) LRT refits of a cell-mode fit.
+        if self.dist_group is not None:
             import torch.distributed as dist
             dist.all_reduce(out, group=self.dist_group)
         return out.cpu().numpy()

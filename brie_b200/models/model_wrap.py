@@ -144,17 +144,16 @@ def _rv_from_engine(eng, m, Xc_model, Xg, intercept_mode):
 
 def _host_pseudo_count_inplace(data, pseudo_count):
     """Side effect of model_wrap.py:113-117 on the caller's dense arrays: where c1 + c2 > 0 add the
-    pseudo-count to c1 and c2 in place.  (The fit itself reads the device tiles.)"""
-    try:
-        import torch
-        t0, t1 = torch.from_numpy(data[0]), torch.from_numpy(data[1])     # views of the caller's memory
-        inc = ((t0 + t1) > 0).to(t0.dtype).mul_(pseudo_count)
-        t0.add_(inc)
-        t1.add_(inc.to(t1.dtype))
-    except (TypeError, ValueError, RuntimeError):      # read-only / unsupported dtype: numpy semantics
-        idx = data[0] + data[1] > 0
-        for i in range(2):
-            data[i][idx] = data[i][idx] + pseudo_count
+    pseudo-count to c1 and c2 in place.  (The fit itself reads the device tiles.)
+
+    Read-only arrays (`np.load(mmap_mode='r')`, `writeable=False`) raise the ValueError numpy's
+    in-place assignment raises in the reference; they are never written through another view."""
+    for d in data[:2]:
+        if not d.flags.writeable:
+            raise ValueError("assignment destination is read-only")
+    idx = data[0] + data[1] > 0
+    for i in range(2):
+        np.add(data[i], pseudo_count, out=data[i], where=idx, casting='unsafe')
 
 
 def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
@@ -180,6 +179,7 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     n_eval = keyargs.pop('n_eval', 500)
     MC_size = keyargs.pop('MC_size', 1)
     target = keyargs.pop('target', "ELBO")                          # reaches BRIE2.fit through **keyargs (:144)
+    host_side_effect = keyargs.pop('host_side_effect', True)
     for k in ('optimizer', 'learn_rate', 'verbose'):                # accepted and ignored (:214-237)
         keyargs.pop(k, None)
 
@@ -212,7 +212,9 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
         h2d_bytes += nb
     ingest.add_pseudo_count(tiles, pseudo_count)
     # the reference also leaves the pseudo-count in the caller's dense arrays (in-place add, :115-117)
-    if all(isinstance(d, np.ndarray) for d in data[:2]):
+    # -- only where the reference's arrays are the caller's own: fitBRIE's event batches are copies
+    # (fancy indexing with a range, :245-249), so fitBRIE passes host_side_effect=False for its slices
+    if host_side_effect and all(isinstance(d, np.ndarray) for d in data[:2]):
         _host_pseudo_count_inplace(data, pseudo_count)
     t_ph = _tick("pseudo_count+ingest", t_ph)
     if Xc is None:
@@ -254,48 +256,59 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     data = tiles
     cell_mode = intercept_mode.upper() == 'CELL'
     T = len(test_masks)
-    # NB the reference builds the refits WITHOUT intercept_mode (model_wrap.py:174-178), so
-    # they always use the default per-event ('gene') intercept/sigma layout.
+    # Engine plan: (masks, model ids, intercept mode) per FitEngine.  One engine holds the base model and as
+    # many refits as one launch batches (BRIE_MAX_MODELS = 32); a one-vs-rest LRT over more covariates than
+    # that runs the remaining refits in further engines, one after the other, over the same device tiles.
+    # NB the reference builds the refits WITHOUT intercept_mode (model_wrap.py:174-178), so they always use
+    # the default per-event ('gene') intercept/sigma layout: a cell-mode base model gets an engine of its own.
+    from .._lib import BRIE_MAX_MODELS
+    plan = []
     if cell_mode and T > 0:
-        engines = [FitEngine(data, masks=[base_cols], model_ids=[0], intercept_mode=intercept_mode, **common),
-                   FitEngine(data, masks=test_masks, model_ids=list(range(1, T + 1)), intercept_mode='gene',
-                             **common)]
-        where = [(0, 0)] + [(1, i) for i in range(T)]
-        inits = [None if init_objs is None else init_objs[:1], None if init_objs is None else init_objs[1:]]
+        plan.append(([base_cols], [0], intercept_mode))
+        first_tests = 0
     else:
-        engines = [FitEngine(data, masks=[base_cols] + test_masks, model_ids=list(range(T + 1)),
-                             intercept_mode=intercept_mode, **common)]
-        where = [(0, i) for i in range(T + 1)]
-        inits = [init_objs]
+        first_tests = min(T, BRIE_MAX_MODELS - 1)
+        plan.append(([base_cols] + test_masks[:first_tests], list(range(first_tests + 1)), intercept_mode))
+    for t0 in range(first_tests, T, BRIE_MAX_MODELS):
+        t1 = min(t0 + BRIE_MAX_MODELS, T)
+        plan.append((test_masks[t0:t1], list(range(1 + t0, 1 + t1)), 'gene'))
     t_ph = _tick("engine_setup", t_ph)
-    for eng, io in zip(engines, inits):
+
+    brie_results = None
+    n_iter_rows, lg_tests, wc_last, launches = [None] * (T + 1), [None] * T, [None] * T, 0
+    for masks_e, ids_e, mode_e in plan:
+        eng = FitEngine(data, masks=masks_e, model_ids=ids_e, intercept_mode=mode_e, **common)
+        io = None if init_objs is None else [init_objs[i] for i in ids_e]
         eng.fit(n_eval=n_eval, init_objs=io, **keyargs)             # :144, :180
-    t_ph = _tick("fit", t_ph)
-    if timing is not None:
-        for eng in engines:
+        t_ph = _tick("fit", t_ph)
+        if timing is not None:
             for k, v in eng.phase_s.items():
                 timing[k] = timing.get(k, 0.0) + v
-
-    e0, m0 = engines[where[0][0]], where[0][1]
-    brie_results = _rv_from_engine(e0, m0, Xc[:, base_cols], Xg, intercept_mode)   # :146
-    brie_results.n_iter = np.stack([engines[w[0]].n_iter[w[1]] for w in where], axis=0)  # (1+T, groups)
-    brie_results.launch_count = sum(e.launch_count for e in engines)
+        for j, mid in enumerate(ids_e):
+            n_iter_rows[mid] = eng.n_iter[j]
+            if mid == 0:
+                brie_results = _rv_from_engine(eng, j, Xc[:, base_cols], Xg, intercept_mode)   # :146
+            else:
+                lg_tests[mid - 1] = eng.loss_gene[j].cpu().numpy()
+                if not full:
+                    wc_last[mid - 1] = eng.Wc[j, len(eng.masks[j]) - 1, :Ng].cpu().numpy()[None, :]
+        launches += eng.launch_count
+        del eng                                                     # the next engine reuses the state memory
+        t_ph = _tick("posterior+d2h", t_ph)
+    brie_results.n_iter = np.stack(n_iter_rows, axis=0)             # (1+T, groups)
+    brie_results.launch_count = launches
     brie_results.h2d_bytes = h2d_bytes
-    t_ph = _tick("posterior+d2h", t_ph)
     brie_results.timing = timing
     if T == 0:                                                      # :152-153
         return brie_results
 
     ELBO_gain = np.zeros((Ng, T), dtype=np.float32)                 # :155
     for ii, idx_k in enumerate(LRT_index):
-        et, mt = engines[where[1 + ii][0]], where[1 + ii][1]
-        lg_test = et.loss_gene[mt].cpu().numpy()
         if full:
-            ELBO_gain[:, ii] = lg_test - brie_results.loss_gene     # :183
+            ELBO_gain[:, ii] = lg_tests[ii] - brie_results.loss_gene     # :183
         else:
-            ELBO_gain[:, ii] = brie_results.loss_gene - lg_test     # :185
-            wc_last = et.Wc[mt, len(et.masks[mt]) - 1, :Ng].cpu().numpy()[None, :]
-            brie_results.cell_coeff = np.append(brie_results.cell_coeff, wc_last, axis=0)  # :186-187
+            ELBO_gain[:, ii] = brie_results.loss_gene - lg_tests[ii]     # :185
+            brie_results.cell_coeff = np.append(brie_results.cell_coeff, wc_last[ii], axis=0)  # :186-187
     brie_results.ELBO_gain = ELBO_gain                              # H1 vs NUll
     brie_results.pval = chi2.sf(2 * ELBO_gain, df=1)                # :190
     fdr = fdr_by_group(brie_results.pval, group_size, event_offset)
@@ -427,7 +440,7 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
                 intercept=intercept, intercept_mode=intercept_mode,
                 LRT_index=LRT_index, pseudo_count=pseudo_count, sigma=sigma,
                 base_mode=base_mode, tau_prior=tau_prior, group_size=_n_gene,
-                event_offset=e0, n_events_total=Ng, **keyargs)
+                event_offset=e0, n_events_total=Ng, host_side_effect=False, **keyargs)
             _t0 = time.perf_counter()
             store.put(e0, _ResVal)
             if getattr(_ResVal, 'timing', None) is not None:
@@ -442,9 +455,12 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
         for k, v in store.finish().items():
             setattr(ResVal, k, v)
     elif world > 1:
-        # shared per-cell parameters: shard events, all-reduce the shared gradients (engine.py)
+        # shared per-cell parameters: shard events, the library all-reduces the shared gradients
+        # every step (engine.py / csrc/brie_comm.cu).  The dense (cells, events) outputs go into their
+        # column range of the output arrays / memory maps; only per-event vectors are gathered.
         lo, hi = event_shards(Ng, world, 1)[rank]
         _idx = range(lo, hi)
+        store = LayerStore(Nc, Ng, out_dir, rank, world, dist)
         _count_layers = [adata.layers[_key][:, _idx] for _key in layer_keys]
         _effLen = adata.varm['effLen'][_idx, :] if 'effLen' in adata.varm else None
         local = fit_BRIE_matrix(
@@ -453,9 +469,12 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
             pseudo_count=pseudo_count, sigma=sigma, base_mode=base_mode,
             tau_prior=tau_prior, event_offset=lo, n_events_total=Ng,
             dist_group=dist.group.WORLD, **keyargs)
+        store.put(lo, local, checkpoint=False)
         parts = [None] * world
         dist.all_gather_object(parts, local)
         ResVal = _merge_shared(parts)
+        for k, v in store.finish().items():
+            setattr(ResVal, k, v)
     else:                                                           # :261-269
         _count_layers = [adata.layers[_key] for _key in layer_keys]
         _effLen = adata.varm['effLen'] if 'effLen' in adata.varm else None

@@ -94,6 +94,11 @@ class AnnDataLite:
             d["var/" + c] = np.asarray(self.var[c])
         for grp, dic in (("obsm", self.obsm), ("varm", self.varm), ("layers", self.layers)):
             for k, v in dic.items():
+                if isinstance(v, np.memmap) and v.filename is not None:
+                    # a memory-mapped (cells, events) output layer (fitBRIE out_dir): keep it where it is
+                    # and store its path -- embedding it would densify 80 GB per layer at atlas scale
+                    d[grp + "_memmap/" + k] = np.asarray(str(v.filename))
+                    continue
                 d[grp + "/" + k] = v.toarray() if issparse(v) else np.asarray(v)
         d["uns"] = np.array(self.uns, dtype=object)
         np.savez_compressed(path, **d)
@@ -105,5 +110,10 @@ class AnnDataLite:
         z = np.load(path, allow_pickle=True)
         obs = pd.DataFrame({k[4:]: z[k] for k in z.files if k.startswith("obs/")}, index=z["obs_index"])
         var = pd.DataFrame({k[4:]: z[k] for k in z.files if k.startswith("var/")}, index=z["var_index"])
-        pick = lambda g: {k[len(g) + 1:]: z[k] for k in z.files if k.startswith(g + "/")}
+        def pick(g):
+            out = {k[len(g) + 1:]: z[k] for k in z.files if k.startswith(g + "/")}
+            for k in z.files:
+                if k.startswith(g + "_memmap/"):
+                    out[k[len(g) + 8:]] = np.load(str(z[k]), mmap_mode='r')
+            return out
         return cls(z["X"], obs, var, pick("obsm"), pick("varm"), pick("layers"), z["uns"].item())

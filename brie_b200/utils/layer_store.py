@@ -82,7 +82,7 @@ class LayerStore:
         if self.world > 1:
             self.dist.barrier()
 
-    def put(self, e0, result):
+    def put(self, e0, result, checkpoint=True):
         """Move the big arrays of one chunk result into columns [e0, e0 + result.Ng) and leave
         (cells, 0) stubs behind, so BRIE_RV.concate only appends the per-event vectors."""
         e1 = e0 + result.Ng
@@ -90,7 +90,7 @@ class LayerStore:
             self.arrays[k][:, e0:e1] = getattr(result, k)
             setattr(result, k, np.zeros((self.shape[0], 0), np.float32))
         self.ranges.append((e0, e1))
-        if self.out_dir is not None:        # checkpoint: big arrays on disk first, then the marker file
+        if self.out_dir is not None and checkpoint:   # big arrays on disk first, then the marker file
             for a in self.arrays.values():
                 a.flush()
             tmp = self._chunk_path(e0, e1) + ".tmp"

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BRIE_ABI_VERSION 4
+#define BRIE_ABI_VERSION 5
 #define BRIE_MAX_MODELS 32
 #define BRIE_MAX_KC 16
 #define BRIE_MAX_KG 8
@@ -165,6 +165,29 @@ int brie_fit_set_active_blocks(brie_fit* fit, const int32_t* blk_ids, int64_t bl
  * applies Adam to Wg / per-cell intercept / sigma_log. */
 int brie_fit_step_phase(brie_fit* fit, int32_t phase, int32_t trace_slot, void* stream);
 int brie_fit_cell_grad(brie_fit* fit, float** ptr, int64_t* n_floats);
+
+/* Event-sharded fits with shared per-cell parameters WITHOUT a host round trip per step: a
+ * communicator spanning the ranks that hold the event shards of one fit (one process per GPU).
+ * The reference has no counterpart (single process); the exchange follows from its model: Wg is
+ * (Nc, Kg), shared by all events (model_TFProb.py:85, 124-125), and with intercept_mode 'cell'
+ * so are intercept and sigma_log (:53-55), while events are the shard axis (model_wrap.py:241-260).
+ *  brie_comm_unique_id : rank 0 fills 128 bytes (ncclUniqueId) that the caller ships to every rank;
+ *  brie_comm_create    : collective over all `world` ranks, on the calling thread's current device;
+ *  brie_fit_set_comm   : from now on brie_fit_run_steps all-reduces (sum) the per-cell gradient
+ *                        buffer (M, Nc, Kg + 2 * cell_mode) with NCCL on `stream` between the fused
+ *                        step kernel and the per-cell Adam update; NULL detaches.
+ *  brie_comm_allreduce_f32 / _f64 : in-place sum on `stream` (group loss traces, tests).
+ * NCCL is bound at run time (dlopen of libnccl.so.2, preferring the copy already in the process);
+ * without it these return BRIE_ERR_UNSUPPORTED and brie_comm_nccl_version() returns 0. */
+typedef struct brie_comm brie_comm; /* opaque */
+int brie_comm_nccl_version(void);
+int brie_comm_unique_id(void* id_host /* 128 bytes */);
+int brie_comm_create(const void* id_host, int32_t rank, int32_t world, brie_comm** out);
+int brie_comm_destroy(brie_comm* comm);
+int brie_comm_allreduce_f32(brie_comm* comm, float* buf, int64_t n, void* stream);
+int brie_comm_allreduce_f64(brie_comm* comm, double* buf, int64_t n, void* stream);
+int64_t brie_comm_allreduce_count(const brie_comm* comm);
+int brie_fit_set_comm(brie_fit* fit, brie_comm* comm);
 
 /* Replaces the 500x `get_loss(axis=0)` averaging (model_TFProb.py:261-264):
  * loss_gene[m, g] = sum_c KL - mean over n_eval evaluations, each with `mc_size` fresh-noise

@@ -218,3 +218,43 @@ def test_published_reference_tables_pin_pval_and_fdr(table):
     # the pin has teeth: one BH over the whole column does not reproduce the table
     whole = np.stack([fdr_bh(pval[:, j]) for j in range(fdr.shape[1])], 1)
     assert np.mean(np.abs(whole - fdr) > 1e-2 * fdr) > 0.3
+
+
+def test_kl_term_known_answers_by_numerical_integration():
+    """The KL term of get_loss (model_TFProb.py:208) pinned by mathematics, independently of TFP's algebra:
+    KL(q || p) = integral q(z) [log q(z) - log p(z)] dz evaluated by adaptive quadrature in float64, for
+    posteriors / priors spanning the ranges the fit visits (Z_std = exp(N(0,1)) at init, sigma 0.3..3,
+    |mu - m| up to 9).  Also against torch.distributions' closed form (a second, independent library)."""
+    from scipy.integrate import quad
+    from oracle.brie2_oracle import kl_normal_normal
+    rng = np.random.default_rng(5)
+    cases = [(0.0, 0.0, 0.0, 0.0), (9.0, np.log(20.0), -2.0, np.log(0.3)), (-9.0, -3.0, 1.0, 1.0)]
+    cases += [(rng.uniform(-9, 9), rng.normal(0, 1.2), rng.normal(0, 3), rng.normal(0, 0.6)) for _ in range(40)]
+    for mu, lam, m, tau in cases:
+        s, sig = np.exp(lam), np.exp(tau)
+
+        def integrand(z):
+            lq = -0.5 * ((z - mu) / s) ** 2 - lam - 0.5 * np.log(2 * np.pi)
+            lp = -0.5 * ((z - m) / sig) ** 2 - tau - 0.5 * np.log(2 * np.pi)
+            return np.exp(lq) * (lq - lp)
+        num, _ = quad(integrand, mu - 12 * s, mu + 12 * s, epsabs=1e-13, epsrel=1e-13, limit=400)
+        got = float(kl_normal_normal(np.float64(mu), np.float64(lam), np.float64(m), np.float64(tau)))
+        assert abs(got - num) <= 1e-9 * max(1.0, abs(num)), (mu, lam, m, tau, got, num)
+        t = torch.distributions.kl_divergence(
+            torch.distributions.Normal(torch.tensor(mu, dtype=torch.float64), torch.tensor(s, dtype=torch.float64)),
+            torch.distributions.Normal(torch.tensor(m, dtype=torch.float64), torch.tensor(sig, dtype=torch.float64)))
+        assert abs(got - float(t)) <= 1e-10 * max(1.0, abs(got))
+    # and the same term inside the oracle's loss: zero counts => loss_gene is the column sum of the KL
+    Nc, Ng = 6, 5
+    om = OracleBRIE2(Nc, Ng, 0, 0, None, None, 'gene', None, dtype=np.float64, seed=3)
+    zero = [np.zeros((Nc, Ng)), np.zeros((Nc, Ng))]
+    _, lg, _ = om.loss_and_grads(zero, np.zeros((1, Nc, Ng)), want_grads=False)
+    want = np.zeros(Ng)
+    for c in range(Nc):
+        for g in range(Ng):
+            mu, lam, m, tau = om.p['Z_loc'][c, g], om.p['Z_std_log'][c, g], om.p['intercept'][0, g], om.p['sigma_log'][0, g]
+            s, sig = np.exp(lam), np.exp(tau)
+            want[g] += quad(lambda z: np.exp(-0.5 * ((z - mu) / s) ** 2 - lam - 0.5 * np.log(2 * np.pi)) * (
+                (-0.5 * ((z - mu) / s) ** 2 - lam) - (-0.5 * ((z - m) / sig) ** 2 - tau)),
+                mu - 12 * s, mu + 12 * s, epsabs=1e-13, epsrel=1e-13, limit=400)[0]
+    assert np.abs(lg - want).max() <= 1e-9 * np.abs(want).max()
