@@ -125,10 +125,12 @@ __device__ __forceinline__ void adam_update(float& x, float& m, float& v, float 
   x -= (m * alpha) * rcp_approx(sqrt_approx(v) + kAdamEps);
 }
 
-// Packed FP32 pairs (sm_100a FFMA2 / FADD2 / FMUL2: one issue slot, two IEEE-rounded results).  Experimental path
-// of the dense phases of the step kernel, compiled in with -DBRIE_F32X2=1 (default off until A/B-ed on hardware).
+// Packed FP32 pairs (sm_100a FFMA2 / FADD2 / FMUL2: one issue slot, two IEEE-rounded results) in the dense phases
+// and the Monte-Carlo samples of the step kernel.  A/B on one B200 against the scalar build (-DBRIE_F32X2=0),
+// profiles/r2_ab_f32x2.md: C2 unchanged (0.936), C3 with loss trace 0.930 -> 0.949, C4 0.947 -> 0.958 / with loss
+// trace 0.900 -> 0.923, Kc 16 0.730 -> 0.761 / 0.700 -> 0.742; the whole parity suite passes on either build.
 #ifndef BRIE_F32X2
-#define BRIE_F32X2 0
+#define BRIE_F32X2 1
 #endif
 #define BRIE_F2_BINARY(name, ptx)                                                                          \
   __device__ __forceinline__ float2 name(float2 a, float2 b) {                                             \

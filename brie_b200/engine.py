@@ -136,7 +136,7 @@ class FitEngine:
         self.counts = [padded(c) for c in counts]
         # read counts are non-negative; the step kernel relies on it (an element whose counts sum to zero has
         # zeros in every layer, brie_kernels.cuh phase B)
-        if min(float(c.min()) for c in self.counts) < 0:
+        if float(torch.stack([c.min() for c in self.counts]).min()) < 0:      # one device sync for all layers
             raise ValueError("brie_b200: count layers must be non-negative")
         self.h2d_bytes = sum(int(np.prod(c.shape)) * 4 for c in counts)
         if effLen is not None:
@@ -445,37 +445,44 @@ class FitEngine:
             tr = self.group_trace(n_stage).astype(np.float32)        # (M, NG, n_stage)
         else:
             tr = np.zeros((M, NG, 0), np.float32)
-        traces = [[tr[m, g] for g in range(NG)] for m in range(M)]
         t_ph = tick("fit.schedule", t_ph)
+        # Stop rule per (model, reference batch), vectorised over all of them (20 000 batches of one event at
+        # 1M cells): only the last d2 losses of a batch enter the rule; the pieces of its trace are kept as
+        # views and joined once at the end.
         n_iter = np.full((M, NG), min_iter, np.int64)                # :247
         d1 = int(min(50, add_iter / 2))
         d2 = d1 * 2
         active = np.ones((M, NG), bool)
+        tail = tr[:, :, tr.shape[2] - min(d2, tr.shape[2]):]         # (M, NG, <= d2)
+        pieces = [(active.copy(), tr)]
         while True:                                                  # :250-258
-            for m in range(M):
-                for g in range(NG):
-                    if active[m, g]:
-                        L = traces[m][g]
-                        a_, b_ = L[-d2:-d1], L[-d1:]      # an empty window compares False, as NaN does in the reference
-                        cond = (a_.mean() - b_.mean() > epsilon_conv) if (a_.size and b_.size) else False
-                        active[m, g] = bool(cond) and n_iter[m, g] < max_iter
+            a_, b_ = tail[:, :, :max(tail.shape[2] - d1, 0)], tail[:, :, max(tail.shape[2] - d1, 0):]
+            if d1 > 0 and a_.shape[2] > 0 and b_.shape[2] > 0:
+                with np.errstate(invalid='ignore'):
+                    cond = a_.mean(axis=2, dtype=np.float32) - b_.mean(axis=2, dtype=np.float32) > epsilon_conv
+            else:                                                    # an empty window compares False, as NaN does in the reference
+                cond = np.zeros((M, NG), bool)
+            active &= cond & (n_iter < max_iter)
             if not active.any():
                 break
             if not self.run_steps_gathered(active, add_iter):
                 self.set_active_groups(active)
                 self.run_steps(add_iter, 0)
             tr = self.group_trace(add_iter).astype(np.float32)
-            for m in range(M):
-                for g in range(NG):
-                    if active[m, g]:
-                        traces[m][g] = np.concatenate([traces[m][g], tr[m, g]])
-                        n_iter[m, g] += add_iter
+            pieces.append((active.copy(), tr))
+            new_tail = np.concatenate([tail, tr], axis=2)[:, :, -d2:] if d2 > 0 else tail
+            tail = np.where(active[:, :, None], new_tail, tail if tail.shape[2] == new_tail.shape[2] else new_tail)
+            n_iter[active] += add_iter
         self.set_active_groups(np.ones((M, NG), bool))
         t_ph = tick("fit.extensions", t_ph)
         self.n_iter = n_iter
-        self.traces = traces
-        # BRIE_RV.concate appends the per-batch traces end to end (model_wrap.py:61)
-        self.losses = [np.concatenate(traces[m]) if NG else np.zeros(0, np.float32) for m in range(M)]
+        # BRIE_RV.concate appends the per-batch traces end to end (model_wrap.py:61): for every model, batch after
+        # batch, each batch's last-stage trace followed by the rounds it was still active in
+        self.pieces = pieces
+        self.losses = []
+        for m in range(M):
+            parts = [p[m, g] for g in range(NG) for (a, p) in pieces if a[m, g]]
+            self.losses.append(np.concatenate(parts) if parts else np.zeros(0, np.float32))
         self.loss_gene = self.eval_loss_gene(n_eval)                 # :261-264
         tick("fit.loss_gene", t_ph)
         return self.losses

@@ -6,12 +6,12 @@
 mkdir -p gpurun_out
 cat > /tmp/brie_sanitize_case.py <<'PY'
 import sys, os
-sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), 'tests'))
 import numpy as np, torch
 import __graft_entry__ as g
 g.smoke()
 from brie_b200.models import fit_BRIE_matrix
-from tests.util import make_problem, make_lrt_problem
+from util import make_problem, make_lrt_problem
 # wide covariates (2 events per lane) + gene features + per-cell intercept: every reduction path of the step kernel
 data, effLen, Xc, Xg = make_problem(70, 45, 9, 5, False, 2, seed=3)
 fit_BRIE_matrix([x.copy() for x in data], Xc=Xc, Xg=Xg, intercept_mode='cell', LRT_index=[], min_iter=12, max_iter=12,

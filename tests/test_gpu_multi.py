@@ -38,6 +38,15 @@ r = fitBRIE(ad, Xc=Xc, Xg=Xg, LRT_index=[], intercept_mode='cell', layer_keys=['
             min_iter=360, max_iter=860, MC_size=2, n_eval=20)
 out['b'] = dict(Psi=r.Psi, gc=ad.obsm['gene_coeff'], ic=ad.obsm['intercept'], sg=ad.obsm['sigma'],
                 lg=np.asarray(ad.var['loss_gene']), losses=np.asarray(ad.uns['brie_losses']), cc=ad.varm['cell_coeff'])
+# (c) per-cell intercept + gene features + LRT: the reference's refits fall back to the per-event intercept layout
+#     (model_wrap.py:174-178); sharded, every engine's stop rule must see the loss summed over all ranks
+data, effLen, Xc, Xg = make_problem(80, 64, 1, 2, False, 2, seed=6)
+ad = AnnDataLite(X=data[0], layers={'spliced': data[0], 'unspliced': data[1]})
+r = fitBRIE(ad, Xc=Xc, Xg=Xg, LRT_index=None, intercept_mode='cell', layer_keys=['spliced', 'unspliced'], seed=2,
+            min_iter=360, max_iter=1860, MC_size=2, n_eval=20)
+out['c'] = dict(n_iter=r.n_iter, gain=r.ELBO_gain, Psi=r.Psi, losses=np.asarray(ad.uns['brie_losses']))
+from brie_b200 import comm
+out['allreduces'] = sum(c.allreduce_count() for c in comm._COMMS.values())
 if world == 1 or dist.get_rank() == 0:
     pickle.dump(out, open(%(out)r, "wb"))
 if world > 1:
@@ -82,6 +91,13 @@ def test_sharded_fitBRIE_matches_single_gpu(tmp_path):
         tol_med = 1e-5 if k == 'Psi' else 5e-3
         assert np.median(d) < tol_med and np.quantile(d, 0.99) < 2e-2 and d.max() < 5e-2, k
     assert np.abs(b1['lg'] - b2['lg']).max() <= 1e-3 * np.abs(b1['lg']).max()
+    # the library issued the data-path collective itself: one all-reduce per optimisation step of (b) and (c)
+    assert res[1]['allreduces'] == 0 and res[2]['allreduces'] >= 360 + 2 * 360
+    c1, c2 = res[1]['c'], res[2]['c']
+    print("cell-mode + LRT n_iter: 1 GPU %s, 2 GPUs %s" % (c1['n_iter'].tolist(), c2['n_iter'].tolist()))
+    assert np.array_equal(c1['n_iter'], c2['n_iter'])            # same stop decisions whatever the world size
+    assert c1['losses'].shape == c2['losses'].shape
+    assert np.quantile(np.abs(c1['Psi'] - c2['Psi']), 0.99) < 1e-3
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")

@@ -333,3 +333,51 @@ def test_gathered_vs_in_place_cost_model():
     c = cols(2500, 2, 5, 0.1)
     c[0] = c[0][:0]
     assert gathered_round_is_cheaper(c, 2500, 100000, 3, 500)
+
+
+def test_npz_container_references_memmapped_layers(tmp_path):
+    """brie-quant --outDir: the dense output layers are .npy memory maps; the output container stores their
+    paths instead of embedding 80 GB arrays, and reading it maps them again."""
+    from brie_b200.utils.anndata_lite import AnnDataLite
+    rng = np.random.default_rng(0)
+    X = rng.poisson(1.0, (6, 9)).astype(np.float32)
+    ad = AnnDataLite(X=X, layers={'isoform1': X.copy()})
+    p = str(tmp_path / "Psi.npy")
+    mm = np.lib.format.open_memmap(p, mode='w+', dtype=np.float32, shape=X.shape)
+    mm[:] = rng.uniform(size=X.shape)
+    mm.flush()
+    ad.layers['Psi'] = np.load(p, mmap_mode='r+')
+    out = str(tmp_path / "out.npz")
+    ad.write_npz(out)
+    assert os.path.getsize(out) < 4096                                   # the map is referenced, not embedded
+    z = np.load(out, allow_pickle=True)
+    assert 'layers_memmap/Psi' in z.files and 'layers/Psi' not in z.files
+    back = AnnDataLite.read_npz(out)
+    assert isinstance(back.layers['Psi'], np.memmap)
+    assert np.array_equal(np.asarray(back.layers['Psi']), np.asarray(mm))
+    assert np.array_equal(back.layers['isoform1'], X)
+
+
+def test_host_pseudo_count_side_effect_semantics():
+    """model_wrap.py:113-117 mutates the caller's dense arrays; read-only arrays raise (numpy's own error in the
+    reference) and are never written through another view; fitBRIE's batch slices are left alone."""
+    from brie_b200.models.model_wrap import _host_pseudo_count_inplace
+    a = np.array([[0, 2, 0], [1, 0, 0]], np.float32)
+    b = np.array([[0, 0, 0], [3, 0, 1]], np.float32)
+    _host_pseudo_count_inplace([a, b, None], 0.01)
+    assert np.allclose(a, [[0, 2.01, 0], [1.01, 0, 0.01]]) and np.allclose(b, [[0, 0.01, 0], [3.01, 0, 1.01]])
+    ro = a.copy()
+    ro.flags.writeable = False
+    keep = ro.copy()
+    with pytest.raises(ValueError, match="read-only"):
+        _host_pseudo_count_inplace([ro, b, None], 0.01)
+    assert np.array_equal(ro, keep)
+
+
+def test_cli_has_outdir_and_resume_flags():
+    import subprocess
+    out = subprocess.run([sys.executable, "-m", "brie_b200.bin.quant", "--help"], capture_output=True, text=True,
+                         cwd=ROOT, timeout=120)
+    assert out.returncode == 0
+    for flag in ("--outDir", "--resume", "--LRTindex", "--testBase", "--interceptMode", "--MCsize", "--batchSize"):
+        assert flag in out.stdout, flag
