@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(len(UNITS)) as ex:
         objs = list(ex.map(compile_unit, UNITS))
-    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-ldl"], check=True)
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", out] + objs + ["-ldl", "-lcublas"], check=True)
     return OUT
 
 

@@ -1,5 +1,6 @@
 // Host side of the brie_b200 C ABI (include/brie_b200.h): argument checking,
 // launch geometry, kernel dispatch.  No persistent device allocations.
+#include <cublas_v2.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -59,6 +60,10 @@ struct brie_fit {
   int32_t n_blk[BRIE_MAX_MODELS] = {0};
   int blk_tiles = 0;
   brie_comm* comm = nullptr;   // event-sharded fit with shared per-cell parameters: G is all-reduced every step
+  // wide designs (Kc > BRIE_MAX_KC or Kg > BRIE_MAX_KG): covariate contractions as GEMMs around the fused kernel
+  bool wide = false;
+  size_t off_PM = 0, off_R = 0, off_gWc = 0;   // (M, Nc, ld), (M, Nc, ld), (M, Kc, ld) in scratch
+  cublasHandle_t blas = nullptr;
 };
 
 using namespace brie;
@@ -70,7 +75,7 @@ constexpr int kMaxDevices = 64;
 bool kc_supported(int k) { return k == 0 || k == 1 || k == 2 || k == 4 || k == 8 || k == 16; }
 bool kg_supported(int k) { return k == 0 || k == 4 || k == 8; }
 
-template <int KC, int KG, bool CELL, bool LOSS>
+template <int KC, int KG, bool CELL, bool LOSS, bool EXT = false>
 cudaError_t launch_step(const StepArgs& a, dim3 grid, cudaStream_t s) {
   // per instantiation and per device: opt in to > 48 KB dynamic shared memory (the attribute is per device)
   static bool configured[kMaxDevices] = {false};
@@ -78,13 +83,86 @@ cudaError_t launch_step(const StepArgs& a, dim3 grid, cudaStream_t s) {
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= kMaxDevices || !configured[dev]) {
-    e = cudaFuncSetAttribute(elbo_step_kernel<KC, KG, CELL, LOSS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             step_smem_bytes(KC, KG, CELL, LOSS));
+    e = cudaFuncSetAttribute(elbo_step_kernel<KC, KG, CELL, LOSS, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             step_smem_bytes(KC, KG, CELL, LOSS, EXT));
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < kMaxDevices) configured[dev] = true;
   }
-  elbo_step_kernel<KC, KG, CELL, LOSS><<<grid, kThreads, step_smem_bytes(KC, KG, CELL, LOSS), s>>>(a);
+  elbo_step_kernel<KC, KG, CELL, LOSS, EXT><<<grid, kThreads, step_smem_bytes(KC, KG, CELL, LOSS, EXT), s>>>(a);
   return cudaGetLastError();
+}
+
+cudaError_t dispatch_step_wide(const StepArgs& a, bool cell, bool loss, dim3 grid, cudaStream_t s) {
+  if (cell)
+    return loss ? launch_step<0, 0, true, true, true>(a, grid, s) : launch_step<0, 0, true, false, true>(a, grid, s);
+  return loss ? launch_step<0, 0, false, true, true>(a, grid, s) : launch_step<0, 0, false, false, true>(a, grid, s);
+}
+
+const char* blas_status(cublasStatus_t st) {
+  switch (st) {
+    case CUBLAS_STATUS_SUCCESS: return "success";
+    case CUBLAS_STATUS_NOT_INITIALIZED: return "not initialized";
+    case CUBLAS_STATUS_ALLOC_FAILED: return "allocation failed";
+    case CUBLAS_STATUS_INVALID_VALUE: return "invalid value";
+    case CUBLAS_STATUS_ARCH_MISMATCH: return "arch mismatch";
+    case CUBLAS_STATUS_EXECUTION_FAILED: return "execution failed";
+    case CUBLAS_STATUS_INTERNAL_ERROR: return "internal error";
+    case CUBLAS_STATUS_NOT_SUPPORTED: return "not supported";
+    default: return "unknown";
+  }
+}
+#define BRIE_BLAS(call)                                                                               \
+  do {                                                                                                \
+    cublasStatus_t st_ = (call);                                                                      \
+    if (st_ != CUBLAS_STATUS_SUCCESS)                                                                 \
+      return brie::fail(BRIE_ERR_CUDA, "%s failed: cuBLAS %s (%s:%d)", #call, blas_status(st_), __FILE__, __LINE__); \
+  } while (0)
+
+// Wide form, before the fused kernel: PM[m] (Nc x ld, row-major) = Xc[m] (Nc x Kc) Wc[m] (Kc x ld) + Wg[m] (Nc x Kg) Xg^T
+// (Z_prior, model_TFProb.py:121-125).  Row-major arrays are handed to cuBLAS as their column-major transposes.
+int wide_prior_mean(brie_fit* f, cudaStream_t s) {
+  const brie_fit_desc& d = f->d;
+  float* scratch = (float*)f->buf.scratch;
+  const float one = 1.f, zero = 0.f;
+  BRIE_BLAS(cublasSetStream(f->blas, s));
+  const int64_t plane = d.n_cells * d.ld;
+  for (int m = 0; m < d.n_models; ++m) {
+    float* PM = scratch + f->off_PM + (size_t)m * plane;
+    if (d.Kc > 0)
+      BRIE_BLAS(cublasSgemm(f->blas, CUBLAS_OP_N, CUBLAS_OP_N, (int)d.ld, (int)d.n_cells, d.Kc, &one,
+                            f->buf.Wc + (size_t)m * d.Kc * d.ld, (int)d.ld,
+                            f->buf.Xc + (size_t)m * d.n_cells * d.Kc, d.Kc, &zero, PM, (int)d.ld));
+    else
+      BRIE_CUDA(cudaMemsetAsync(PM, 0, (size_t)plane * sizeof(float), s));
+    if (d.Kg > 0)
+      BRIE_BLAS(cublasSgemm(f->blas, CUBLAS_OP_T, CUBLAS_OP_N, (int)d.n_events, (int)d.n_cells, d.Kg, &one,
+                            f->buf.Xg, d.Kg, f->buf.Wg + (size_t)m * d.n_cells * d.Kg, d.Kg, &one, PM, (int)d.ld));
+  }
+  f->launches += d.n_models * ((d.Kc > 0) + (d.Kg > 0));
+  return BRIE_OK;
+}
+
+// Wide form, after the fused kernel: d loss / d Wc[m] = -Xc[m]^T R[m] (Kc x ld) and d loss / d Wg[m] = -R[m] Xg (Nc x Kg),
+// the latter written into the per-cell gradient buffer G (M, Nc, Kg + 2 * cell_mode) the all-reduce and the per-cell
+// Adam update read.
+int wide_gradients(brie_fit* f, cudaStream_t s) {
+  const brie_fit_desc& d = f->d;
+  float* scratch = (float*)f->buf.scratch;
+  const float minus = -1.f, zero = 0.f;
+  BRIE_BLAS(cublasSetStream(f->blas, s));
+  const int64_t plane = d.n_cells * d.ld;
+  for (int m = 0; m < d.n_models; ++m) {
+    const float* R = scratch + f->off_R + (size_t)m * plane;
+    if (d.Kc > 0)
+      BRIE_BLAS(cublasSgemm(f->blas, CUBLAS_OP_N, CUBLAS_OP_T, (int)d.ld, d.Kc, (int)d.n_cells, &minus, R, (int)d.ld,
+                            f->buf.Xc + (size_t)m * d.n_cells * d.Kc, d.Kc, &zero,
+                            scratch + f->off_gWc + (size_t)m * d.Kc * d.ld, (int)d.ld));
+    if (d.Kg > 0)
+      BRIE_BLAS(cublasSgemm(f->blas, CUBLAS_OP_N, CUBLAS_OP_N, d.Kg, (int)d.n_cells, (int)d.n_events, &minus, f->buf.Xg,
+                            d.Kg, R, (int)d.ld, &zero, scratch + f->off_G + (size_t)m * d.n_cells * f->ncell, f->ncell));
+  }
+  f->launches += d.n_models * ((d.Kc > 0) + (d.Kg > 0));
+  return BRIE_OK;
 }
 
 template <int KC, int KG>
@@ -141,10 +219,15 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
   if (d.n_cells >= ((int64_t)1 << 32) || d.event_offset < 0 || d.event_offset + d.ld >= ((int64_t)1 << 32))
     return fail(BRIE_ERR_ARG, "cell / event index exceeds the 32-bit RNG counter words");
   if (d.n_models < 1 || d.n_models > BRIE_MAX_MODELS) return fail(BRIE_ERR_ARG, "n_models out of range");
-  if (!kc_supported(d.Kc))
-    return fail(BRIE_ERR_UNSUPPORTED, "Kc must be one of 0,1,2,4,8,16 (pad Xc with zero columns)");
-  if (!kg_supported(d.Kg))
-    return fail(BRIE_ERR_UNSUPPORTED, "Kg must be one of 0,4,8 (pad Xg with zero columns)");
+  if (d.Kc < 0 || d.Kg < 0 || d.Kc > BRIE_MAX_K_WIDE || d.Kg > BRIE_MAX_K_WIDE)
+    return fail(BRIE_ERR_ARG, "Kc and Kg must be in [0, %d]", BRIE_MAX_K_WIDE);
+  const bool wide = d.Kc > BRIE_MAX_KC || d.Kg > BRIE_MAX_KG;
+  if (!wide && !kc_supported(d.Kc))
+    return fail(BRIE_ERR_UNSUPPORTED, "Kc must be one of 0,1,2,4,8,16 (pad Xc with zero columns) or above 16 (wide form)");
+  if (!wide && !kg_supported(d.Kg))
+    return fail(BRIE_ERR_UNSUPPORTED, "Kg must be one of 0,4,8 (pad Xg with zero columns) or above 8 (wide form)");
+  if (wide && d.target != BRIE_TARGET_ELBO)
+    return fail(BRIE_ERR_UNSUPPORTED, "target marginLik is limited to Kc <= %d and Kg <= %d", BRIE_MAX_KC, BRIE_MAX_KG);
   if (d.mc_size < 1 || d.mc_size > 4096) return fail(BRIE_ERR_ARG, "mc_size out of range");
   if (d.n_layers != 2 && d.n_layers != 3) return fail(BRIE_ERR_ARG, "n_layers must be 2 or 3");
   if (d.trace_cap < 0) return fail(BRIE_ERR_ARG, "trace_cap must be >= 0");
@@ -153,13 +236,15 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
     return fail(BRIE_ERR_ARG, "target must be BRIE_TARGET_ELBO or BRIE_TARGET_MARGINLIK");
   for (int m = 0; m < d.n_models; ++m) {
     if (d.model_id[m] < 0 || d.model_id[m] >= 4096) return fail(BRIE_ERR_ARG, "model_id must be in [0, 4096)");
-    if ((d.xc_mask[m] >> d.Kc) != 0) return fail(BRIE_ERR_ARG, "xc_mask has bits beyond Kc");
+    if (!wide && (d.xc_mask[m] >> d.Kc) != 0) return fail(BRIE_ERR_ARG, "xc_mask has bits beyond Kc");
+    if (wide && (d.xc_width[m] < 0 || d.xc_width[m] > d.Kc)) return fail(BRIE_ERR_ARG, "xc_width out of range");
   }
   brie_fit* f = new (std::nothrow) brie_fit();
   if (!f) return fail(BRIE_ERR_ARG, "out of host memory");
   f->d = d;
+  f->wide = wide;
   memset(&f->buf, 0, sizeof f->buf);
-  const int n_tiles = (int)ceil_div(d.ld, step_tile_cols(d.Kc));   // 128 events per tile, 64 when Kc = 16
+  const int n_tiles = (int)ceil_div(d.ld, step_tile_cols(wide ? 0 : d.Kc, wide ? 0 : d.Kg));   // 128 events per tile, 64 when Kc = 16
   // rows per CTA: up to 256 (fewer row-chunk partials for event_update_kernel) while keeping
   // >= ~10 waves of 2 CTAs/SM (tail effect); small problems go down to one row per warp
   int rows = 256;
@@ -185,8 +270,9 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
     return fail(BRIE_ERR_UNSUPPORTED, "grid too large (%lld row chunks, %d column tiles)", (long long)n_chunks,
                 n_tiles);
   }
-  f->nev_max = d.Kc + 2 + 1;
+  f->nev_max = (wide ? 0 : d.Kc) + 2 + 1;
   f->ncell = d.Kg + (d.cell_mode ? 2 : 0);
+  const int ncell_part = wide ? (d.cell_mode ? 2 : 0) : f->ncell;   // what the fused kernel leaves per cell and tile
   f->sz.rows_per_cta = rows;
   f->sz.n_row_chunks = (int)n_chunks;
   f->sz.n_col_tiles = n_tiles;
@@ -195,9 +281,18 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
   f->off_part_ev = off;
   off += (size_t)n_chunks * d.n_models * f->nev_max * d.ld;
   f->off_part_cell = off;
-  off += (size_t)n_tiles * d.n_models * d.n_cells * f->ncell;
+  off += (size_t)n_tiles * d.n_models * d.n_cells * ncell_part;
   f->off_G = off;
   off += (size_t)d.n_models * d.n_cells * f->ncell;
+  off = (off + 3) / 4 * 4;                     // 16-byte alignment of what follows
+  if (wide) {
+    f->off_PM = off;
+    off += (size_t)d.n_models * d.n_cells * d.ld;
+    f->off_R = off;
+    off += (size_t)d.n_models * d.n_cells * d.ld;
+    f->off_gWc = off;
+    off += (size_t)d.n_models * (d.Kc > 0 ? d.Kc : 1) * d.ld;
+  }
   f->sz.scratch_bytes = (off + 4) * sizeof(float);
   f->sz.adam_small_floats =
       (size_t)2 * d.n_models * (d.Kc + 2) * d.ld + (size_t)2 * d.n_models * d.n_cells * (d.Kg + 2);
@@ -206,6 +301,7 @@ int brie_fit_create(const brie_fit_desc* desc, brie_fit** out) {
 }
 
 int brie_fit_destroy(brie_fit* fit) {
+  if (fit && fit->blas) cublasDestroy(fit->blas);
   if (fit) {
     for (cudaEvent_t e : fit->ev0) cudaEventDestroy(e);
     for (cudaEvent_t e : fit->ev1) cudaEventDestroy(e);
@@ -273,8 +369,21 @@ int brie_fit_bind(brie_fit* fit, const brie_fit_buffers* b) {
     if (b->counts_model_stride < 0 || b->counts_model_stride % 4 != 0 || b->efflen_model_stride < 0)
       return fail(BRIE_ERR_ARG, "model strides must be >= 0 (counts: a multiple of 4 floats)");
   }
+  if (fit->wide && (b->event_ids || b->counts_model_stride || b->efflen_model_stride))
+    return fail(BRIE_ERR_UNSUPPORTED, "gathered sub-fits are limited to Kc <= %d", BRIE_MAX_KC);
   fit->buf = *b;
   fit->bound = true;
+  if (fit->wide) {   // residuals of never-active (padding) columns must be finite for the gradient GEMMs
+    float* scratch = (float*)b->scratch;
+    const size_t plane = (size_t)d.n_models * d.n_cells * d.ld;
+    BRIE_CUDA(cudaMemset(scratch + fit->off_PM, 0, plane * sizeof(float)));
+    BRIE_CUDA(cudaMemset(scratch + fit->off_R, 0, plane * sizeof(float)));
+    if (!fit->blas) {
+      cublasStatus_t st = cublasCreate(&fit->blas);
+      if (st != CUBLAS_STATUS_SUCCESS) return fail(BRIE_ERR_CUDA, "cublasCreate failed: %s", blas_status(st));
+      cublasSetMathMode(fit->blas, CUBLAS_PEDANTIC_MATH);   // plain fp32 FMA accumulation: no TF32, no split-K surprises
+    }
+  }
   return BRIE_OK;
 }
 
@@ -299,7 +408,7 @@ int brie_fit_init_params(brie_fit* f, float intercept_const, float sigma_const, 
     int kk = 0;
     for (int k = 0; k < d.Kc; ++k) {
       float* dst = f->buf.Wc + ((int64_t)m * d.Kc + k) * d.ld;
-      if ((d.xc_mask[m] >> k) & 1u) {
+      if (f->wide ? k < d.xc_width[m] : ((d.xc_mask[m] >> k) & 1u) != 0) {
         normals_kernel<<<grid_1d(d.ld, 256), 256, 0, s>>>(d.seed, BRIE_PHASE_INIT, mid, BRIE_INIT_WC, 1, 1, d.ld,
                                                          d.event_offset, kk, d.ld, dst);
         ++kk;
@@ -380,7 +489,8 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
     const double t = (double)f->t;
     f->alpha = (float)((double)f->lr * sqrt(1.0 - pow(0.999, t)) / (1.0 - pow(0.9, t)));
     const bool margin = d.target == BRIE_TARGET_MARGINLIK;
-    int nev = d.Kc + (d.cell_mode ? 0 : 2) + (loss ? 1 : 0);
+    const int kc_kernel = f->wide ? 0 : d.Kc;     // covariates the fused kernel contracts itself
+    int nev = kc_kernel + (d.cell_mode ? 0 : 2) + (loss ? 1 : 0);
     int cell_tiles = f->sz.n_col_tiles;
     if (margin && f->buf.event_ids) return fail(BRIE_ERR_UNSUPPORTED, "marginLik on a gathered sub-fit");
     if (margin) {
@@ -440,20 +550,37 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
       for (int m = 0; m < M; ++m) a.n_blk[m] = f->n_blk[m];
       grid.y = (unsigned)(f->blk_tiles > 0 ? f->blk_tiles : 1);
     }
+    if (f->wide) {
+      a.PM = scratch + f->off_PM;
+      a.R = scratch + f->off_R;
+      int rc = wide_prior_mean(f, s);
+      if (rc) return rc;
+    }
     const bool timed = f->ev_used < (int)f->ev0.size();
     if (timed) BRIE_CUDA(cudaEventRecord(f->ev0[f->ev_used], s));
-    BRIE_CUDA(dispatch_step(a, d.Kc, d.Kg, d.cell_mode != 0, loss, grid, s));
+    if (f->wide)
+      BRIE_CUDA(dispatch_step_wide(a, d.cell_mode != 0, loss, grid, s));
+    else
+      BRIE_CUDA(dispatch_step(a, d.Kc, d.Kg, d.cell_mode != 0, loss, grid, s));
     if (timed) BRIE_CUDA(cudaEventRecord(f->ev1[f->ev_used++], s));
     f->launches += 1;
+    if (f->wide) {
+      int rc = wide_gradients(f, s);
+      if (rc) return rc;
+    }
     }
 
-    if (nev > 0) {
+    if (nev > 0 || (f->wide && d.Kc > 0)) {
       EventArgs e;
       memset(&e, 0, sizeof e);
       e.ld = d.ld; e.Ng = d.n_events; e.M = M; e.KC = d.Kc; e.NEV = nev; e.n_chunks = f->sz.n_row_chunks;
-      e.idx_gb = d.cell_mode ? -1 : d.Kc;
-      e.idx_gt = d.cell_mode ? -1 : d.Kc + 1;
-      e.idx_loss = (loss || margin) ? d.Kc + (d.cell_mode ? 0 : 2) : -1;   // trace written only if trace_slot >= 0
+      e.idx_gb = d.cell_mode ? -1 : kc_kernel;
+      e.idx_gt = d.cell_mode ? -1 : kc_kernel + 1;
+      e.idx_loss = (loss || margin) ? kc_kernel + (d.cell_mode ? 0 : 2) : -1;   // trace written only if trace_slot >= 0
+      if (f->wide) {
+        e.wc_grad = scratch + f->off_gWc;
+        for (int m = 0; m < M; ++m) e.xc_width[m] = d.xc_width[m];
+      }
       e.train_b = d.train_intercept; e.train_tau = d.train_sigma;
       e.trace_slot = trace_slot; e.trace_cap = d.trace_cap;
       e.alpha = f->alpha;
@@ -475,10 +602,14 @@ int brie_fit_step_phase(brie_fit* f, int32_t phase, int32_t trace_slot, void* st
       c.model_mask = mmask;
       c.part_cell = scratch + f->off_part_cell;
       c.G = scratch + f->off_G;
-      const dim3 g3((unsigned)ceil_div(d.n_cells * f->ncell, 256), M);
-      cell_reduce_kernel<<<g3, 256, 0, s>>>(c);
-      BRIE_CUDA(cudaGetLastError());
-      f->launches += 1;
+      c.n_part = f->wide ? (d.cell_mode ? 2 : 0) : f->ncell;   // wide: d/dWg is already in G (wide_gradients)
+      c.part_off = f->wide ? d.Kg : 0;
+      if (c.n_part > 0) {
+        const dim3 g3((unsigned)ceil_div(d.n_cells * c.n_part, 256), M);
+        cell_reduce_kernel<<<g3, 256, 0, s>>>(c);
+        BRIE_CUDA(cudaGetLastError());
+        f->launches += 1;
+      }
     }
     f->step_open = true;
     return BRIE_OK;
@@ -546,7 +677,7 @@ int brie_fit_set_active_blocks(brie_fit* f, const int32_t* blk_ids, int64_t blk_
     return fail(BRIE_ERR_UNSUPPORTED, "column compaction needs per-event parameters only (Kg = 0, gene intercept) and target ELBO");
   if (d.ld % 8 != 0) return fail(BRIE_ERR_ARG, "column compaction needs ld %% 8 == 0");
   if (!n_blk_host || blk_stride < 1) return fail(BRIE_ERR_ARG, "n_blk_host and blk_stride required");
-  const int bpt = step_tile_cols(d.Kc) / kBlkCols;
+  const int bpt = step_tile_cols(f->wide ? 0 : d.Kc, f->wide ? 0 : d.Kg) / kBlkCols;
   int tiles = 0;
   for (int m = 0; m < d.n_models; ++m) {
     if (n_blk_host[m] < 0 || n_blk_host[m] > blk_stride || (int64_t)n_blk_host[m] * kBlkCols > d.ld)
@@ -607,6 +738,42 @@ int brie_fit_posterior(brie_fit* f, int32_t model, float* Psi, float* Psi95CI, f
       f->buf.Z_loc + model * plane, f->buf.Z_std_log + model * plane, plane, Psi, Psi95CI, Z_std);
   BRIE_CUDA(cudaGetLastError());
   f->launches += 1;
+  return BRIE_OK;
+}
+
+int brie_fit_element_terms(brie_fit* f, int32_t model, const float* c1, const float* c2, const float* c3,
+                           int32_t mc_size, uint32_t noise_step, int32_t margin, float* loglik, float* kl,
+                           float* prior_mean, void* stream) {
+  if (!f || !f->bound) return fail(BRIE_ERR_ARG, "fit not bound");
+  if (model < 0 || model >= f->d.n_models) return fail(BRIE_ERR_ARG, "model index out of range");
+  if (loglik && (!c1 || !c2)) return fail(BRIE_ERR_ARG, "count tiles required for loglik");
+  if (loglik && (mc_size < 1 || mc_size > 4096)) return fail(BRIE_ERR_ARG, "mc_size out of range");
+  if (f->buf.event_ids) return fail(BRIE_ERR_UNSUPPORTED, "element terms are evaluated on the parent fit");
+  const brie_fit_desc& d = f->d;
+  TermsArgs a;
+  memset(&a, 0, sizeof a);
+  a.Nc = d.n_cells; a.Ng = d.n_events; a.ld = d.ld; a.event_offset = d.event_offset; a.seed = d.seed;
+  a.c[0] = c1; a.c[1] = c2; a.c[2] = c3;
+  a.eff = f->buf.efflen3; a.Xc = f->buf.Xc; a.Xg = f->buf.Xg;
+  a.Zl = f->buf.Z_loc; a.Zs = f->buf.Z_std_log;
+  a.Wc = f->buf.Wc; a.b = f->buf.intercept; a.tau = f->buf.sigma_log; a.Wg = f->buf.Wg;
+  a.loglik = loglik; a.kl = kl; a.prior_mean = prior_mean;
+  a.M = d.n_models; a.m = model; a.S = mc_size; a.KC = d.Kc; a.KG = d.Kg; a.cell_mode = d.cell_mode;
+  a.margin = margin != 0; a.model_id = d.model_id[model]; a.noise_step = noise_step;
+  element_terms_kernel<<<grid_1d(d.n_cells * d.ld, 256), 256, 0, (cudaStream_t)stream>>>(a);
+  BRIE_CUDA(cudaGetLastError());
+  f->launches += 1;
+  return BRIE_OK;
+}
+
+int brie_resample_counts(uint64_t seed, int64_t n_cells, int64_t n_events, int64_t ld, int64_t event_offset,
+                         const float* total, const float* psi, const float* efflen3, float* c1, float* c2, float* c3,
+                         void* stream) {
+  if (n_cells <= 0 || n_events <= 0 || ld < n_events) return fail(BRIE_ERR_ARG, "bad shape");
+  if (!total || !psi || !c1 || !c2) return fail(BRIE_ERR_ARG, "null argument");
+  resample_counts_kernel<<<grid_1d(n_cells * ld, 256), 256, 0, (cudaStream_t)stream>>>(
+      seed, n_cells, n_events, ld, event_offset, total, psi, efflen3, c1, c2, c3);
+  BRIE_CUDA(cudaGetLastError());
   return BRIE_OK;
 }
 

@@ -72,6 +72,11 @@ struct StepArgs {
   const int32_t* ev_ids;   // (M, ld)
   int64_t c_mstride;       // floats between the count tiles of consecutive models
   int64_t eff_mstride;     // floats between the (3, ld) length tables of consecutive models
+  // Wide designs (EXT instantiations): the covariate part of the prior mean, Xc Wc + Wg Xg^T, arrives as a dense
+  // (M, Nc, ld) array computed by a GEMM before the launch, and r = (mu - m) / sigma^2 leaves as one, for the
+  // GEMMs that turn it into d loss / d Wc = -Xc^T r and d loss / d Wg = -r Xg (brie_abi.cu).
+  const float* PM;
+  float* R;
 };
 
 constexpr int kBlkCols = 8;   // events per compaction block = one 32-byte sector of every f32 array
@@ -264,8 +269,9 @@ struct StepTraits {
 
 // Events per lane of the step kernel: 4 (one 16-byte access per array) while the per-event
 // accumulators and weights of a lane, 2 x KC x EPL registers, fit next to the rest; the wide
-// covariate case (KC = 16) runs with 2 events per lane (8-byte accesses, 64-event tiles).
-__host__ __device__ constexpr int step_epl(int KC) { return KC > 8 ? 2 : 4; }
+// covariate cases (KC = 16, and KC = 8 together with gene features, whose per-cell accumulators come on top)
+// run with 2 events per lane (8-byte accesses, 64-event tiles) -- no instantiation spills to local memory.
+__host__ __device__ constexpr int step_epl(int KC, int KG = 0) { return (KC > 8 || (KC == 8 && KG > 0)) ? 2 : 4; }
 
 template <int EPL> struct LaneVec;
 template <> struct LaneVec<4> { using type = float4; };
@@ -319,7 +325,7 @@ __device__ __forceinline__ void cp_async_lane(uint32_t dst_smem, const void* src
 constexpr int kQueueFields = 1;   // tile column of the element; its data is read from, and its results written to, the row's ring slots
 constexpr int kRingArrays = 9;    // Z_loc, Z_std_log, c1, c2, c3, m_loc, v_loc, m_std, v_std
 constexpr int kRingStages = 2;
-__host__ __device__ constexpr int step_tile_cols(int KC) { return 32 * step_epl(KC); }
+__host__ __device__ constexpr int step_tile_cols(int KC, int KG = 0) { return 32 * step_epl(KC, KG); }
 // Per-event constants of a column tile (Wc rows, Xg columns, intercept, sigma_log, 1/sigma^2) stay in
 // registers for narrow designs; wider ones (Kc + Kg >= 3) keep them in shared memory and re-read them
 // every row, so they are not live across the Monte-Carlo phase (no spills).  A/B on one box
@@ -337,18 +343,21 @@ __host__ __device__ constexpr int step_n_consts(int KC, int KG, bool CELL, bool 
   return step_consts_in_smem(KC, KG, LOSS) ? KC + KG + (CELL ? 0 : 3) : 0;
 }
 constexpr int kRowConstSlots = 32;   // per warp and ring stage: Xc[c, :], Wg[c, :], per-cell intercept / sigma_log of the row
-__host__ __device__ constexpr int step_smem_bytes(int KC, int KG, bool CELL, bool LOSS) {
-  return (kWarps * kRingStages * kRingArrays + kWarps * kQueueFields + 7 + step_n_consts(KC, KG, CELL, LOSS)) *
-             step_tile_cols(KC) * 4 +
+__host__ __device__ constexpr int step_smem_bytes(int KC, int KG, bool CELL, bool LOSS, bool EXT = false) {
+  return (kWarps * kRingStages * (kRingArrays + (EXT ? 1 : 0)) + kWarps * kQueueFields + 7 +
+          step_n_consts(KC, KG, CELL, LOSS)) *
+             step_tile_cols(KC, KG) * 4 +
          kWarps * kRingStages * kRowConstSlots * 4;
 }
 
-template <int KC, int KG, bool CELL, bool LOSS>
+template <int KC, int KG, bool CELL, bool LOSS, bool EXT = false>
 __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(const StepArgs a) {
+  static_assert(!EXT || (KC == 0 && KG == 0), "the wide-design form takes all covariates through PM / R");
+  constexpr int NRA = kRingArrays + (EXT ? 1 : 0);   // ring arrays per stage (EXT: + the prior-mean tile)
   using T = StepTraits<KC, KG, CELL, LOSS>;
   constexpr int NEV = T::NEV;
   constexpr int NCELL = T::NCELL;
-  constexpr int EPL = step_epl(KC);
+  constexpr int EPL = step_epl(KC, KG);
   constexpr int TC = 32 * EPL;              // events per warp row segment (column tile)
   constexpr bool kSm = step_consts_in_smem(KC, KG, LOSS);
   using Vec = typename LaneVec<EPL>::type;
@@ -383,10 +392,10 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     for (int j = 0; j < EPL; ++j) act |= (a.active[(int64_t)m * a.ld + g0 + j] != 0 ? 1u : 0u) << j;
   }
   extern __shared__ __align__(128) float smem[];
-  float* s_ring = smem + warp * (kRingStages * kRingArrays * TC);
-  uint32_t* q = reinterpret_cast<uint32_t*>(smem + kWarps * kRingStages * kRingArrays * TC +
+  float* s_ring = smem + warp * (kRingStages * NRA * TC);
+  uint32_t* q = reinterpret_cast<uint32_t*>(smem + kWarps * kRingStages * NRA * TC +
                                             warp * kQueueFields * TC);
-  float(*s_L)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * kRingArrays * TC +
+  float(*s_L)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * NRA * TC +
                                                    kWarps * kQueueFields * TC);
   uint32_t* s_ev = reinterpret_cast<uint32_t*>(s_L + 6);   // global event id of each tile column (RNG counter word)
   float(*s_k)[TC] = s_L + 7;                // kSm: rows Wc[0..KC), Xg[0..KG), then (gene mode) b, tau, 1/sigma^2
@@ -400,7 +409,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   for (int t = 0; t < KGB; ++t) pk |= ((lane >> (4 - t)) & 1) << (KGB - 1 - t);
   constexpr int NRC = KC + KG + (CELL ? 2 : 0);   // per-row (cell) constants: Xc[c, :], Wg[c, :], b[c], tau[c]
   static_assert(NRC <= kRowConstSlots, "row constants must fit one slot per lane");
-  float* s_rc = smem + (kWarps * kRingStages * kRingArrays + kWarps * kQueueFields + 7 +
+  float* s_rc = smem + (kWarps * kRingStages * NRA + kWarps * kQueueFields + 7 +
                         step_n_consts(KC, KG, CELL, LOSS)) * TC +
                 warp * (kRingStages * kRowConstSlots);
 
@@ -453,6 +462,8 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   float* const bA1 = a.aZ + mplane + cta_off;
   float* const bA2 = a.aZ + 2 * mplane + cta_off;
   float* const bA3 = a.aZ + 3 * mplane + cta_off;
+  const float* const bPM = EXT ? a.PM + cta_off : nullptr;
+  float* const bR = EXT ? a.R + cta_off : nullptr;
   const int64_t cnt_off = (int64_t)m * a.c_mstride + row_begin * a.ld;
   const float* const bC0 = a.c[0] + cnt_off;
   const float* const bC1 = a.c[1] + cnt_off;
@@ -470,7 +481,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   auto issue_row = [&](int lr, int stage) {       // lr: row index within the CTA
     const bool ok = act != 0 && lr < n_rows;
     const uint32_t rel = ok ? (uint32_t)lr * ld32 + col32 : 0u;
-    const uint32_t dst = ring_lane + stage * (kRingArrays * TC * 4);
+    const uint32_t dst = ring_lane + stage * (NRA * TC * 4);
     cp_async_lane<EPL * 4>(dst + 0 * TC * 4, bZl + rel, ok);
     cp_async_lane<EPL * 4>(dst + 1 * TC * 4, bZs + rel, ok);
     cp_async_lane<EPL * 4>(dst + 2 * TC * 4, bC0 + rel, ok);
@@ -480,6 +491,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     cp_async_lane<EPL * 4>(dst + 6 * TC * 4, bA1 + rel, ok);
     cp_async_lane<EPL * 4>(dst + 7 * TC * 4, bA2 + rel, ok);
     cp_async_lane<EPL * 4>(dst + 8 * TC * 4, bA3 + rel, ok);
+    if (EXT) cp_async_lane<EPL * 4>(dst + 9 * TC * 4, bPM + rel, ok);
     if (NRC > 0) {
       // The row's warp-uniform constants ride in the same commit group, one float per lane.  (As plain
       // loads issued a row ahead they shared a scoreboard with the tile constants loaded before the loop,
@@ -555,8 +567,11 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       if (CELL) { b_row = rc[KC + KG]; tau_row = rc[KC + KG + 1]; }
       __syncwarp();                       // all lanes have read them before any lane's next prefetch overwrites the slot two rows on
     }
-    const Vec* st = reinterpret_cast<const Vec*>(s_ring + stage * (kRingArrays * TC)) + lane;
-    float mu[EPL], lam[EPL], c1[EPL], c2[EPL], c3[EPL];
+    const Vec* st = reinterpret_cast<const Vec*>(s_ring + stage * (NRA * TC)) + lane;
+    float mu[EPL], lam[EPL], c1[EPL], c2[EPL], c3[EPL], pmx[EPL];
+#pragma unroll
+    for (int j = 0; j < EPL; ++j) pmx[j] = 0.f;
+    if (EXT) vec_get<EPL>(st[9 * 32], pmx);
     vec_get<EPL>(st[0 * 32], mu);
     vec_get<EPL>(st[1 * 32], lam);
     vec_get<EPL>(st[2 * 32], c1);
@@ -594,6 +609,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       const float2 tj = CELL ? f2_splat(tau_row) : make_float2(tau[j0], tau[j1]);
       const float2 i2 = CELL ? f2_splat(is2_row) : make_float2(is2[j0], is2[j1]);
       float2 pm = CELL ? f2_splat(b_row) : make_float2(bb[j0], bb[j1]);
+      if (EXT) pm = f2_add(pm, make_float2(pmx[j0], pmx[j1]));
 #pragma unroll
       for (int k = 0; k < KC; ++k) pm = f2_fma(f2_splat(xc[k]), make_float2(wc[k][j0], wc[k][j1]), pm);
 #pragma unroll
@@ -646,6 +662,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       const float tj = CELL ? tau_row : tau[j];
       const float i2 = CELL ? is2_row : is2[j];
       float pm = CELL ? b_row : bb[j];
+      if (EXT) pm += pmx[j];
 #pragma unroll
       for (int k = 0; k < KC; ++k) pm = fmaf(xc[k], wc[k][j], pm);
 #pragma unroll
@@ -677,6 +694,9 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     }
 #endif
 
+    if (EXT && act != 0)   // r = (mu - m) / sigma^2 of this row, for the gradient GEMMs (frozen lanes keep their old values: unused)
+      __stcs(reinterpret_cast<Vec*>(bR + ((uint32_t)lr * ld32 + col32)), vec_make<EPL>(gmu));
+
     // ---- phase B: compacted Monte-Carlo work ----
     uint32_t bal[EPL];
     int base = 0;
@@ -701,7 +721,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
       for (int j = 0; j < EPL; ++j)
         if ((nz >> j) & 1u) q[base + __popc(nz & ((1u << j) - 1u))] = (uint32_t)(lane * EPL + j);
       __syncwarp();
-      float* rs = s_ring + stage * (kRingArrays * TC);
+      float* rs = s_ring + stage * (NRA * TC);
       for (int k = lane; k < n_items; k += 32) {
         const int col = (int)q[k];
         const float imu = rs[col], is = fast_exp(rs[TC + col]);
@@ -807,7 +827,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
 
   if (NEV > 0) {
     __syncthreads();  // all warps are done with their queues; reuse the memory for the reduction
-    float(*red)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * kRingArrays * TC);
+    float(*red)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * NRA * TC);
     const int64_t gcol = thread_col();
 #pragma unroll
     for (int i = 0; i < NEV; ++i) {
@@ -839,6 +859,9 @@ struct EventArgs {
   const uint8_t* active;
   float* trace;
   uint32_t xc_mask[kMaxModels];
+  // wide designs: d loss / d Wc comes from a GEMM as a dense (M, KC, ld) array, rows [0, xc_width[m]) in use
+  const float* wc_grad;
+  int32_t xc_width[kMaxModels];
 };
 
 constexpr int kMaxNEV = 19;  // BRIE_MAX_KC + 2 + 1
@@ -868,8 +891,8 @@ __global__ void __launch_bounds__(256) event_update_kernel(const EventArgs a) {
   };
   const int64_t mstride = (int64_t)a.M * (a.KC + 2) * a.ld;
   for (int k = 0; k < a.KC; ++k) {
-    if (!((a.xc_mask[m] >> k) & 1u)) continue;
-    const float grad = (float)red(k);
+    if (a.wc_grad ? k >= a.xc_width[m] : !((a.xc_mask[m] >> k) & 1u)) continue;
+    const float grad = a.wc_grad ? a.wc_grad[((int64_t)m * a.KC + k) * a.ld + g] : (float)red(k);
     const int64_t pi = ((int64_t)m * a.KC + k) * a.ld + g;
     const int64_t qi = ((int64_t)m * (a.KC + 2) + k) * a.ld + g;
     float x = a.Wc[pi], mm = a.mom[qi], vv = a.mom[mstride + qi];
@@ -907,17 +930,19 @@ struct CellArgs {
   float* G;            // (M, Nc, NCELL)
   float* Wg; float* b; float* tau;
   float* mom;          // (2, M, Nc, KG + 2)
+  int32_t n_part, part_off;   // the partials hold n_part values per cell, which land at G[.., part_off + j]
 };
 
 __global__ void __launch_bounds__(256) cell_reduce_kernel(const CellArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over Nc * NCELL
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // over Nc * n_part
   const int m = blockIdx.y;
-  if (i >= a.Nc * a.NCELL) return;
+  if (i >= a.Nc * a.n_part) return;
   if (!((a.model_mask >> m) & 1u)) return;
   double s = 0.0;
   for (int t = 0; t < a.n_tiles; ++t)
-    s += (double)a.part_cell[((int64_t)t * a.M + m) * a.Nc * a.NCELL + i];
-  a.G[(int64_t)m * a.Nc * a.NCELL + i] = (float)s;
+    s += (double)a.part_cell[((int64_t)t * a.M + m) * a.Nc * a.n_part + i];
+  const int64_t c = i / a.n_part, j = i % a.n_part;
+  a.G[((int64_t)m * a.Nc + c) * a.NCELL + a.part_off + j] = (float)s;
 }
 
 __global__ void __launch_bounds__(256) cell_update_kernel(const CellArgs a) {
@@ -1119,6 +1144,138 @@ __global__ void __launch_bounds__(256) eval_reduce_kernel(const float* part_ev, 
   out[(int64_t)m * ld + g] = (float)(kl - ll);
 }
 
+// Element-wise terms of the public model API (BRIE2.logLik_MC, Z_prior, the KL inside get_loss;
+// model_TFProb.py:118-127, 130-191, 208) for ONE model, written as dense (Nc, ld) arrays -- the reference
+// returns exactly these (Nc, Ng) tensors.  One warp per 128-event row segment as in eval_loss_kernel; every
+// element draws its own `S` samples (noise counter: phase EVAL, step = noise_step), IEEE-accurate math.
+//   loglik[c, g]     mean_s l(z_s)                      z_s = Z_loc + Z_std eps_s          (:159, :191)
+//                    or log mean_s exp l(z_s)           z_s = prior mean + sigma eps_s     (:157, :189)   (margin)
+//   kl[c, g]         KL(N(Z_loc, Z_std) || N(prior mean, sigma))                                          (:208)
+//   prior_mean[c, g] Xc Wc + Wg Xg^T + intercept                                                          (:118-126)
+struct TermsArgs {
+  int64_t Nc, Ng, ld, event_offset;
+  uint64_t seed;
+  const float* c[3];   // explicit count tiles (the caller's count_layers), c[2] may be null
+  const float* eff;
+  const float* Xc; const float* Xg;
+  const float* Zl; const float* Zs;
+  const float* Wc; const float* b; const float* tau; const float* Wg;
+  float* loglik; float* kl; float* prior_mean;   // any may be null
+  int32_t M, m, S, KC, KG, cell_mode, margin, model_id;
+  uint32_t noise_step;
+};
+
+__global__ void __launch_bounds__(256) element_terms_kernel(const TermsArgs a) {
+  const int64_t total = a.Nc * a.ld;
+  const int m = a.m;
+  const bool eff = a.eff != nullptr;
+  const uint32_t stream0 = brie_stream_word(BRIE_PHASE_EVAL, (uint32_t)a.model_id, 0u);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / a.ld, g = i % a.ld;
+    float o_ll = 0.f, o_kl = 0.f, o_pm = 0.f;
+    if (g < a.Ng) {
+      const float tj = a.cell_mode ? a.tau[(int64_t)m * a.Nc + row] : a.tau[(int64_t)m * a.ld + g];
+      float pm = a.cell_mode ? a.b[(int64_t)m * a.Nc + row] : a.b[(int64_t)m * a.ld + g];
+      for (int k = 0; k < a.KC; ++k)
+        pm = fmaf(a.Xc[((int64_t)m * a.Nc + row) * a.KC + k], a.Wc[((int64_t)m * a.KC + k) * a.ld + g], pm);
+      for (int k = 0; k < a.KG; ++k)
+        pm = fmaf(a.Wg[((int64_t)m * a.Nc + row) * a.KG + k], a.Xg[g * a.KG + k], pm);
+      o_pm = pm;
+      const float mu = a.Zl[(int64_t)m * a.Nc * a.ld + i], lam = a.Zs[(int64_t)m * a.Nc * a.ld + i];
+      if (a.kl) {
+        const float d = lam - tj;
+        const float r0 = (mu - pm) * expf(-tj);
+        o_kl = 0.5f * r0 * r0 + 0.5f * expm1f(2.0f * d) - d;
+      }
+      if (a.loglik) {
+        const float c1 = a.c[0][i], c2 = a.c[1][i], c3 = a.c[2] ? a.c[2][i] : 0.f;
+        const float n = c1 + c2 + c3;
+        float L1 = 1.f, L2 = 1.f, L3 = 0.f;
+        if (eff) { L1 = a.eff[g]; L2 = a.eff[a.ld + g]; L3 = a.eff[2 * a.ld + g]; }
+        const float zc = a.margin ? pm : mu, zs = expf(a.margin ? tj : lam);
+        const float k0 = eff ? fmaf(c1, logf(L1), fmaf(c2, logf(L2), c3 * logf(L3))) : 0.f;
+        float acc = 0.f, mx = -INFINITY, Z = 0.f;
+        if (n > 0.f || a.margin) {
+          for (int s0 = 0; s0 < a.S; s0 += 4) {
+            float eps[4];
+            brie_normals4((uint32_t)(a.event_offset + g), (uint32_t)row, a.noise_step, stream0 + (uint32_t)(s0 >> 2),
+                          a.seed, eps);
+            for (int q = 0; q < 4 && s0 + q < a.S; ++q) {
+              const float z = fmaf(zs, eps[q], zc);
+              const float e = expf(-fabsf(z));
+              const float lsp = fminf(z, 0.f) - log1pf(e);
+              const float inv = 1.0f / (1.0f + e);
+              const float psi = z >= 0.f ? inv : e * inv;
+              const float qq = z >= 0.f ? e * inv : inv;
+              const float D = fmaf(psi, L1, fmaf(qq, L2, L3));
+              const float l = fmaf(c1, lsp, c2 * (lsp - z)) - (eff ? n * logf(D) : 0.f) + k0;
+              if (!a.margin) {
+                acc += l;
+              } else {
+                if (l > mx) { Z *= expf(mx - l); mx = l; }
+                Z += expf(l - mx);
+              }
+            }
+          }
+          o_ll = a.margin ? mx + logf(Z) - logf((float)a.S) : acc / (float)a.S;
+        }
+      }
+    }
+    if (a.loglik) a.loglik[i] = o_ll;
+    if (a.kl) a.kl[i] = o_kl;
+    if (a.prior_mean) a.prior_mean[i] = o_pm;
+  }
+}
+
+// Multinomial resampling of observed read depth (brie/models/simulator.py:54-73): for every cell x event,
+// (c1, c2, c3) ~ Multinomial(total[c, g], Phi), Phi ~ [psi L1, (1 - psi) L2, L3] (:54-62), as two conditional
+// binomials.  Exact Bernoulli counting up to 4096 reads per element, normal approximation beyond.
+__device__ inline int resample_binomial(uint32_t event, uint32_t cell, uint32_t stream, uint64_t seed, uint32_t& ctr,
+                                        int n, float p) {
+  if (n <= 0 || p <= 0.f) return 0;
+  if (p >= 1.f) return n;
+  uint32_t buf[4];
+  if (n > 4096) {
+    brie_philox4x32_10(event, cell, ctr++, stream, (uint32_t)seed, (uint32_t)(seed >> 32), buf);
+    float za, zb;
+    brie_box_muller(buf[0], buf[1], &za, &zb);
+    return min(n, max(0, (int)rintf(n * p + sqrtf(n * p * (1.f - p)) * za)));
+  }
+  int k = 0;
+  for (int i = 0; i < n; i += 4) {
+    brie_philox4x32_10(event, cell, ctr++, stream, (uint32_t)seed, (uint32_t)(seed >> 32), buf);
+    for (int j = 0; j < 4 && i + j < n; ++j) k += brie_u01(buf[j]) < p;
+  }
+  return k;
+}
+
+__global__ void __launch_bounds__(256) resample_counts_kernel(uint64_t seed, int64_t Nc, int64_t Ng, int64_t ld,
+                                                              int64_t event_offset, const float* total,
+                                                              const float* psi, const float* eff, float* c1,
+                                                              float* c2, float* c3) {
+  const int64_t n_el = Nc * ld;
+  const uint32_t stream = brie_stream_word(3u /* BRIE_PHASE_SIM */, 1u, 0u);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_el; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i / ld, g = i % ld;
+    float o1 = 0.f, o2 = 0.f, o3 = 0.f;
+    const int n = g < Ng ? (int)rintf(total[i]) : 0;
+    if (n > 0) {
+      float L1 = 1.f, L2 = 1.f, L3 = 0.f;
+      if (eff) { L1 = eff[g]; L2 = eff[ld + g]; L3 = eff[2 * ld + g]; }
+      const float ps = psi[i];
+      const float p1 = ps * L1, p2 = (1.f - ps) * L2, D = p1 + p2 + L3;
+      uint32_t ctr = 0;
+      const int k1 = resample_binomial((uint32_t)(event_offset + g), (uint32_t)c, stream, seed, ctr, n, p1 / D);
+      const int k2 = (D - p1) > 0.f
+                         ? resample_binomial((uint32_t)(event_offset + g), (uint32_t)c, stream, seed, ctr, n - k1, p2 / (D - p1))
+                         : 0;
+      o1 = (float)k1; o2 = (float)k2; o3 = (float)(n - k1 - k2);
+    }
+    c1[i] = o1; c2[i] = o2;
+    if (c3) c3[i] = o3;
+  }
+}
+
 // Psi = sigmoid(Z_loc); Psi95CI = sigmoid(Z_loc + z975 s) - sigmoid(Z_loc - z975 s)
 // (tfd.LogitNormal(...).quantile, model_TFProb.py:92-106); Z_std = exp(Z_std_log).
 __device__ __forceinline__ float sigmoid_acc(float z) {
@@ -1197,7 +1354,8 @@ struct SimRng {
       brie_philox4x32_10(event, cell, ctr++, stream, (uint32_t)seed, (uint32_t)(seed >> 32), buf);
       have = 4;
     }
-    return buf[--have];
+    --have;   // selects, not a dynamic index: the words stay in registers (no local memory)
+    return have == 3 ? buf[3] : (have == 2 ? buf[2] : (have == 1 ? buf[1] : buf[0]));
   }
   __device__ float uniform() { return brie_u01(next()); }
   __device__ float normal() {

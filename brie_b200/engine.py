@@ -22,11 +22,18 @@ KC_SUPPORTED = (0, 1, 2, 4, 8, 16)
 KG_SUPPORTED = (0, 4, 8)
 
 
+K_WIDE_MAX = 4096
+
+
 def _pad_to(k, allowed, what):
+    """Width of the device arrays for a design of k columns: the next register-resident instantiation, or k itself
+    when the design is wide (covariate contractions as GEMMs around the fused kernel, any width)."""
     for a in allowed:
         if k <= a:
             return a
-    raise ValueError("brie_b200: %s = %d exceeds the supported maximum %d" % (what, k, allowed[-1]))
+    if k > K_WIDE_MAX:
+        raise ValueError("brie_b200: %s = %d exceeds the supported maximum %d" % (what, k, K_WIDE_MAX))
+    return k
 
 
 def _round_up(x, m):
@@ -111,6 +118,14 @@ class FitEngine:
         self.M = len(self.masks)
         self.Kc = _pad_to(max(len(mk) for mk in self.masks), KC_SUPPORTED, "Kc (widest batched model)")
         self.Kg = _pad_to(self.Kg_real, KG_SUPPORTED, "Kg")
+        # wide design: one of the widths is beyond the register-resident instantiations; then BOTH contractions run
+        # as GEMMs and neither width is padded
+        self.wide = self.Kc > KC_SUPPORTED[-1] or self.Kg > KG_SUPPORTED[-1]
+        if self.wide:
+            self.Kc, self.Kg = max(len(mk) for mk in self.masks), self.Kg_real
+            if target != "ELBO":
+                raise ValueError("brie_b200: target 'marginLik' supports at most %d cell covariates and %d gene features"
+                                 % (KC_SUPPORTED[-1], KG_SUPPORTED[-1]))
         self.model_ids = list(range(self.M)) if model_ids is None else [int(i) for i in model_ids]
         self.shared = self.cell_mode or self.Kg_real > 0       # parameters shared across events
         if group_size is None or self.shared:
@@ -178,7 +193,8 @@ class FitEngine:
         d.target = _lib.TARGETS[target]
         for m in range(M):
             d.model_id[m] = self.model_ids[m]
-            d.xc_mask[m] = (1 << len(self.masks[m])) - 1
+            d.xc_mask[m] = 0 if self.wide else (1 << len(self.masks[m])) - 1
+            d.xc_width[m] = len(self.masks[m])
         self.desc = d
         h = C.c_void_p()
         _lib.check(self.lib.brie_fit_create(C.byref(d), C.byref(h)))
@@ -355,7 +371,7 @@ class FitEngine:
         e.g. 100 events at 5k cells, where the per-model count tiles of the gathered form (12 B per
         model instead of 12 B shared) outweigh the few half-empty blocks: the caller then steps in
         place.  `force` skips that cost comparison (tests)."""
-        if self.shared or self.target != "ELBO" or os.environ.get("BRIE_NO_GATHER"):
+        if self.shared or self.wide or self.target != "ELBO" or os.environ.get("BRIE_NO_GATHER"):
             return False
         M, Nc, L = self.M, self.Nc, self.n_layers
         g = (np.arange(self.Ng) + self.event_offset) // self.group_size - self.first_group
@@ -415,6 +431,26 @@ class FitEngine:
             _lib.check(self.lib.brie_fit_posterior(self.h, int(model), outs[0].data_ptr(), outs[1].data_ptr(),
                                                    outs[2].data_ptr(), self._stream()))
         return [o[:, :self.Ng] for o in outs]
+
+    def element_terms(self, model=0, counts=None, mc_size=1, margin=False, loglik=True, kl=False,
+                      prior_mean=False, noise_step=None):
+        """Dense (Nc, Ng) device tensors of the public model API for one model: the Monte-Carlo log-likelihood of
+        every element (BRIE2.logLik_MC, model_TFProb.py:130-191), the KL term of get_loss (:208) and the prior mean
+        (Z_prior, :118-127).  `counts`: device tiles (Nc, ld) to evaluate on (default: the fitted ones).  Every call
+        draws fresh noise (the reference samples anew on every call) unless `noise_step` pins the counter."""
+        if noise_step is None:
+            self._terms_calls = getattr(self, "_terms_calls", 0) + 1
+            noise_step = (1 << 20) + self._terms_calls          # apart from the loss_gene evaluations' counters
+        cs = self.counts if counts is None else counts
+        new = lambda want: torch.empty((self.Nc, self.ld), dtype=torch.float32, device=self.device) if want else None
+        o_ll, o_kl, o_pm = new(loglik), new(kl), new(prior_mean)
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.brie_fit_element_terms(
+                self.h, int(model), cs[0].data_ptr(), cs[1].data_ptr(), cs[2].data_ptr() if len(cs) > 2 else None,
+                int(mc_size), int(noise_step), int(bool(margin)), ptr(o_ll), ptr(o_kl), ptr(o_pm), self._stream()))
+        cut = lambda t: t[:, :self.Ng] if t is not None else None
+        return cut(o_ll), cut(o_kl), cut(o_pm)
 
     # ------------------------------------------------------------------ schedule
     def fit(self, min_iter=1000, max_iter=5000, add_iter=500, epsilon_conv=1e-2, n_eval=500,

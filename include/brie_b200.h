@@ -35,10 +35,11 @@
 extern "C" {
 #endif
 
-#define BRIE_ABI_VERSION 5
+#define BRIE_ABI_VERSION 7
 #define BRIE_MAX_MODELS 32
-#define BRIE_MAX_KC 16
+#define BRIE_MAX_KC 16   /* widest design whose covariate contraction stays in registers / shared memory */
 #define BRIE_MAX_KG 8
+#define BRIE_MAX_K_WIDE 4096 /* any wider Kc or Kg up to this runs the wide form (see brie_fit_desc.Kc) */
 
 #define BRIE_TARGET_ELBO 0
 #define BRIE_TARGET_MARGINLIK 1
@@ -55,8 +56,12 @@ typedef struct brie_fit_desc {
   int64_t event_offset;   /* global index of local event 0 (RNG counters) */
   uint64_t seed;          /* noise / init key */
   int32_t n_models;       /* 1 + number of LRT refits batched (model_wrap.py:156) */
-  int32_t Kc;             /* common (padded) width of the per-model Xc, 0..BRIE_MAX_KC (model_TFProb.py:48) */
-  int32_t Kg;             /* columns of Xg, 0..BRIE_MAX_KG (model_TFProb.py:49) */
+  int32_t Kc;             /* common (padded) width of the per-model Xc (model_TFProb.py:48): 0, 1, 2, 4, 8 or 16 for the
+                             register-resident contraction; anything else up to BRIE_MAX_K_WIDE (or Kg > BRIE_MAX_KG)
+                             selects the WIDE form: prior mean Xc Wc + Wg Xg^T and the gradients -Xc^T r, -r Xg are
+                             GEMMs (cuBLAS SGEMM, fp32) around the fused kernel, which then reads / writes one extra
+                             (cells, events) array each -- the reference accepts any Kc, Kg (:84-85, 121-126) */
+  int32_t Kg;             /* columns of Xg (model_TFProb.py:49): 0, 4 or 8, or the wide form */
   int32_t mc_size;        /* MC_size (model_TFProb.py:130) */
   int32_t n_layers;       /* 2 or 3 count layers (model_TFProb.py:184) */
   int32_t has_efflen;     /* 0: binomial branch :162-167; 1: effLen branch :168-185 */
@@ -69,7 +74,8 @@ typedef struct brie_fit_desc {
                              brie_fit_bind's event_ids keeps its parent's value, so the float32 partial sums over
                              cells associate the same way and its results stay bit-identical to the parent's) */
   int32_t model_id[BRIE_MAX_MODELS]; /* RNG model word of each batched model */
-  uint32_t xc_mask[BRIE_MAX_MODELS]; /* bit k set: column k of Xc[model] is a real covariate */
+  uint32_t xc_mask[BRIE_MAX_MODELS]; /* bit k set: column k of Xc[model] is a real covariate (Kc <= BRIE_MAX_KC) */
+  int32_t xc_width[BRIE_MAX_MODELS]; /* wide form: columns [0, xc_width[model]) of Xc[model] are real covariates */
 } brie_fit_desc;
 
 typedef struct brie_fit_sizes {
@@ -199,6 +205,25 @@ int brie_fit_eval_loss_gene(brie_fit* fit, int32_t n_eval, int32_t mc_size, floa
 /* Replaces the Psi / Psi95CI / Z_std properties (model_TFProb.py:88-106) for one model. */
 int brie_fit_posterior(brie_fit* fit, int32_t model, float* Psi, float* Psi95CI, float* Z_std,
                        void* stream);
+
+/* Replaces the tensors the public model API returns for one model (BRIE2.logLik_MC model_TFProb.py:130-191,
+ * Z_prior :118-127, the KL of get_loss :208), as dense (Nc, ld) arrays; any output may be NULL.
+ *   loglik     : mean over mc_size samples of the element's log-likelihood, z ~ N(Z_loc, Z_std) (:159, :191);
+ *                margin != 0: z ~ the prior, log-mean-exp over the samples (:157, :189)
+ *   kl         : KL(N(Z_loc, Z_std) || N(prior mean, sigma))
+ *   prior_mean : Xc Wc + Wg Xg^T + intercept
+ * c1, c2, c3 are the caller's count tiles ((Nc, ld), c3 may be NULL) -- get_loss / logLik_MC take count_layers
+ * as an argument, not the fitted ones.  Noise: counter (event, cell, noise_step) of the EVAL phase. */
+int brie_fit_element_terms(brie_fit* fit, int32_t model, const float* c1, const float* c2, const float* c3,
+                           int32_t mc_size, uint32_t noise_step, int32_t margin, float* loglik, float* kl,
+                           float* prior_mean, void* stream);
+
+/* Replaces `tfd.Multinomial(total_counts, probs=Phi).sample()` of brie.models.simulator (simulator.py:54-73):
+ * (c1, c2, c3)[c, g] ~ Multinomial(total[c, g], [psi L1, (1 - psi) L2, L3] / sum) with total, psi (Nc, ld) device
+ * arrays (total holds integral values), efflen3 (3, ld) or NULL (L = 1, 1, 0), c3 may be NULL. */
+int brie_resample_counts(uint64_t seed, int64_t n_cells, int64_t n_events, int64_t ld, int64_t event_offset,
+                         const float* total, const float* psi, const float* efflen3, float* c1, float* c2, float* c3,
+                         void* stream);
 
 /* Sum the per-event loss trace over reference batches (model_wrap.py:241-246:
  * group g covers events [g*group_size, (g+1)*group_size) in GLOBAL event index):

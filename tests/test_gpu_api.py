@@ -305,5 +305,109 @@ def test_one_vs_rest_lrt_with_15_covariates_null_base():
     eng = FitEngine([x.copy() for x in data], Xc=Xc, masks=[list(range(15))] + [[k for k in range(15) if k != i]
                                                                                for i in range(1, 15)])
     assert eng.Kc == 16 and eng.sizes.n_col_tiles == 1
+    # beyond 16 columns the design is "wide": contractions as GEMMs around the fused kernel, any width
+    eng = FitEngine([x.copy() for x in data], Xc=np.ones((Nc, 40), np.float32))
+    assert eng.wide and eng.Kc == 40
     with pytest.raises(ValueError, match="exceeds the supported maximum"):
-        FitEngine([x.copy() for x in data], Xc=np.ones((Nc, 40), np.float32))
+        FitEngine([x.copy() for x in data], Xc=np.ones((Nc, 5000), np.float32))
+
+
+def test_BRIE2_public_model_api_matches_oracle():
+    """BRIE2.logLik_MC / get_loss / Z_prior / Z / PsiDist (model_TFProb.py:96-127, 130-211) on the device path,
+    against the oracle with the device's noise; re-exports of brie/models/__init__.py:4."""
+    from oracle import philox_np as px
+    from oracle.brie2_oracle import OracleBRIE2, add_pseudo_count, kl_normal_normal
+    from brie_b200 import models
+    assert all(hasattr(models, n) for n in ("BRIE2", "fitBRIE", "fit_BRIE_matrix", "get_CI95", "BRIE_base_lik", "LogitNormal"))
+    Nc, Ng, seed, S = 70, 53, 6, 4
+    for mode, Kc, Kg, eff, nl in (('gene', 2, 0, True, 3), ('cell', 1, 3, False, 2)):
+        data, effLen, Xc, Xg = make_problem(Nc, Ng, Kc, Kg, eff, nl, seed=4)
+        add_pseudo_count(data, np.float32(0.01))
+        m = models.BRIE2(Nc=Nc, Ng=Ng, Kc=Kc, Kg=Kg, effLen=effLen, intercept=None, intercept_mode=mode, seed=seed)
+        m.fit(data, Xc=Xc, Xg=Xg if Kg else None, min_iter=60, max_iter=60, MC_size=2, n_eval=4, verbose=False)
+        e = m._engine
+        om = OracleBRIE2(Nc, Ng, Kc, Kg, effLen, None, mode, None, dtype=np.float64, seed=seed)
+        om.p['Z_loc'], om.p['Z_std_log'] = m.Z_loc.numpy().astype(np.float64), np.log(m.Z_std.numpy().astype(np.float64))
+        om.p['Wc_loc'], om.p['Wg_loc'] = m.Wc_loc.numpy().astype(np.float64), m.Wg_loc.numpy().astype(np.float64)
+        om.p['intercept'], om.p['sigma_log'] = m.intercept.numpy().astype(np.float64), np.log(m.sigma.numpy().astype(np.float64))
+        om.Xc, om.Xg = Xc.astype(np.float64), Xg.astype(np.float64)
+        # Z_prior / Z / PsiDist
+        zp = m.Z_prior
+        assert np.abs(zp.parameters['loc'] - om.prior_mean()).max() < 2e-5
+        assert zp.sample(3, seed=1).shape == (3, Nc, Ng)
+        assert np.abs(m.Z.loc - om.p['Z_loc']).max() == 0
+        assert np.abs(m.PsiDist.quantile(0.975) - m.PsiDist.quantile(0.025) - m.Psi95CI).max() < 2e-6
+        # logLik_MC with pinned noise counters (element_terms), ELBO and marginLik targets
+        epsf = device_eps_provider(seed, 0, Nc, Ng)
+        for margin in (False, True):
+            ll, kl, _ = e.element_terms(0, mc_size=S, margin=margin, kl=True, noise_step=77)
+            eps = epsf(px.PHASE_EVAL, 77, S).astype(np.float64)
+            c = [np.asarray(x, np.float64) for x in data]
+            if margin:
+                z = om.prior_mean()[None] + (np.exp(om.p['sigma_log']) + np.zeros((Nc, Ng)))[None] * eps
+                ls = om._loglik_samples(c, z)[0]
+                ref = np.log(np.exp(ls - ls.max(0)[None]).mean(0)) + ls.max(0)
+            else:
+                z = om.p['Z_loc'][None] + np.exp(om.p['Z_std_log'])[None] * eps
+                ref = om._loglik_samples(c, z)[0].mean(0)
+            assert np.abs(ll.cpu().numpy() - ref).max() <= 2e-5 * max(np.abs(ref).max(), 1.0), (mode, margin)
+            ref_kl = kl_normal_normal(om.p['Z_loc'], om.p['Z_std_log'], om.prior_mean(), om.p['sigma_log'] + np.zeros((Nc, Ng)))
+            assert np.abs(kl.cpu().numpy() - ref_kl).max() <= 2e-5 * max(ref_kl.max(), 1.0)
+        # the public methods: shapes, reductions and consistency (fresh noise on every call)
+        ll = m.logLik_MC(data, MC_size=64).numpy()
+        assert ll.shape == (Nc, Ng) and (ll <= 1e-6).all()
+        lg = m.get_loss(data, axis=0, MC_size=64).numpy()
+        tot = float(m.get_loss(data, MC_size=64).numpy())
+        assert lg.shape == (Ng,) and m.get_loss(data, axis=1).numpy().shape == (Nc,)
+        ref_lg = om.loss_and_grads(data, epsf(px.PHASE_EVAL, 5, 64), want_grads=False)[1]
+        assert np.abs(lg - ref_lg).max() <= 0.05 * np.abs(ref_lg).max()        # different noise: MC error only
+        assert abs(tot - lg.sum()) <= 0.02 * abs(tot)
+        ml = m.get_loss(data, target="marginLik", axis=0, MC_size=8).numpy()
+        assert ml.shape == (Ng,) and np.isfinite(ml).all()
+        # other count layers than the fitted ones are honoured (get_loss takes count_layers as an argument)
+        zero = [np.zeros_like(x) for x in data]
+        assert np.abs(m.logLik_MC(zero, MC_size=2).numpy()).max() == 0
+
+
+def test_device_simulator_mirrors_reference_semantics():
+    """brie.models.simulator (simulator.py:7-75): counts ~ Multinomial(observed total, Phi) on the device --
+    totals preserved exactly, category frequencies follow Phi, posterior / prior modes, side effects on adata."""
+    from brie_b200.models.simulator import simulator
+    from brie_b200.utils.anndata_lite import AnnDataLite
+    Nc, Ng = 400, 60
+    data, effLen, Xc, _ = make_lrt_problem(Nc, Ng, seed=5)
+    rng = np.random.default_rng(0)
+    Psi = rng.uniform(0.05, 0.95, (1, Ng)).astype(np.float32) * np.ones((Nc, 1), np.float32)
+    ad = AnnDataLite(X=data[0] + data[1] + data[2],
+                     layers={'isoform1': data[0], 'isoform2': data[1], 'ambiguous': data[2], 'Psi': Psi},
+                     varm={'effLen': effLen})
+    sim = simulator(ad, seed=3)
+    tot = data[0] + data[1] + data[2]
+    c = [sim.layers[k] for k in ('isoform1', 'isoform2', 'ambiguous')]
+    assert np.array_equal(c[0] + c[1] + c[2], tot)                       # depth is conserved element by element
+    assert all((x >= 0).all() and np.array_equal(x, np.rint(x)) for x in c)
+    assert sim is not ad and np.array_equal(ad.layers['isoform1'], data[0])      # input counts untouched
+    assert np.array_equal(ad.layers['Psi_sim'], Psi)                     # side effect of simulator.py:42
+    L = effLen[:, [0, 4, 5]]
+    w = np.stack([Psi[0] * L[:, 0], (1 - Psi[0]) * L[:, 1], L[:, 2]], 1)
+    phi = w / w.sum(1, keepdims=True)
+    n_g = tot.sum(0)
+    for k in range(3):                                                   # column frequencies within 5 binomial sd
+        f = c[k].sum(0) / n_g
+        sd = np.sqrt(phi[:, k] * (1 - phi[:, k]) / n_g)
+        assert (np.abs(f - phi[:, k]) < 5 * sd + 1e-6).all(), k
+    assert not np.array_equal(simulator(ad, seed=4).layers['isoform1'], c[0])
+    assert np.array_equal(simulator(ad, seed=3).layers['isoform1'], c[0])        # counter-based: reproducible
+    # prior mode: Psi from the fitted coefficients + N(0, sigma) noise, clipped in logit space
+    ad.obsm['Xc'], ad.varm['cell_coeff'] = Xc, rng.normal(0, 1, (Ng, 1)).astype(np.float32)
+    ad.varm['intercept'] = rng.normal(0, 2, (Ng, 1)).astype(np.float32)
+    ad.varm['sigma'] = np.full((Ng, 1), 0.3, np.float32)
+    sim2 = simulator(ad, mode="prior", seed=1)
+    z0 = Xc @ ad.varm['cell_coeff'].T + ad.varm['intercept'].T
+    assert np.allclose(ad.layers['Psi_sim_noNoise'], 1 / (1 + np.exp(-z0)), atol=1e-6)
+    zs = np.log(ad.layers['Psi_sim'] / (1 - ad.layers['Psi_sim']))
+    assert abs(np.std(zs - z0) - 0.3) < 0.02 and np.abs(zs).max() <= 9.0 + 1e-3
+    assert np.array_equal(sum(sim2.layers[k] for k in ('isoform1', 'isoform2', 'ambiguous')), tot)
+    sim3 = simulator(ad, mode="prior", prior_sigma=1.5, seed=1)
+    zs3 = np.log(ad.layers['Psi_sim'] / (1 - ad.layers['Psi_sim']))
+    assert abs(np.std(np.clip(zs3 - z0, -20, 20)) - 1.5) < 0.1

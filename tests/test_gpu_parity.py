@@ -53,6 +53,11 @@ CASES = [
     ('gene', True, 3, 11, 0, None, None),    # wide covariates: Kc 11 -> 16, two events per lane, 64-event tiles
     ('cell', False, 2, 9, 5, None, None),    # wide covariates + gene features + per-cell intercept
     ('gene', True, 3, 7, 0, None, None),     # Kc 7 -> 8
+    ('gene', True, 3, 8, 4, None, None),     # Kc 8 with gene features: two events per lane (no spills)
+    ('gene', True, 3, 24, 0, None, None),    # WIDE design: Kc 24 > 16 -> contractions as GEMMs around the fused kernel
+    ('cell', False, 2, 3, 20, None, None),   # WIDE: Kg 20 > 8, per-cell intercept
+    ('gene', True, 3, 33, 11, None, None),   # WIDE: both, more than 32 covariates (no bit mask)
+    ('cell', True, 3, 19, 0, None, 1.5),     # WIDE, per-cell intercept, fixed sigma
 ]
 
 
@@ -112,7 +117,8 @@ def test_first_step_loss_and_gradients(mode, eff, n_layers, Kc, Kg, intercept, s
         close(10 * cellp[:, :Kg], grads['Wg_loc'], 'Wg')
 
 
-@pytest.mark.parametrize("mode,eff,n_layers,Kc,Kg,intercept,sigma", [CASES[1], CASES[4], CASES[6], CASES[8]])
+@pytest.mark.parametrize("mode,eff,n_layers,Kc,Kg,intercept,sigma", [CASES[1], CASES[4], CASES[6], CASES[8], CASES[12],
+                                                                     CASES[13]])
 def test_trajectory_parity(mode, eff, n_layers, Kc, Kg, intercept, sigma):
     """60 optimisation steps (2 Adam stages) track the float32 oracle step for step."""
     Nc, Ng, S, seed = 96, 131, 3, 5

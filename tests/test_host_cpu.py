@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 def test_struct_layout_matches_header():
     from brie_b200 import _lib
-    assert C.sizeof(_lib.FitDesc) == 4 * 8 + 8 + 12 * 4 + 32 * 4 + 32 * 4
+    assert C.sizeof(_lib.FitDesc) == 4 * 8 + 8 + 12 * 4 + 32 * 4 + 32 * 4 + 32 * 4
     assert C.sizeof(_lib.FitBuffers) == 20 * 8      # + event_ids, counts_model_stride, efflen_model_stride (ABI 4)
     assert C.sizeof(_lib.FitSizes) == 2 * 8 + 4 * 4
 
@@ -59,13 +59,24 @@ def test_create_validates_arguments(lib):
     assert lib.brie_fit_run_steps(h, 1, -1, None) < 0
     assert b"not bound" in lib.brie_last_error()
     lib.brie_fit_destroy(h)
-    for bad in (dict(ld=50), dict(ld=62), dict(Kc=3), dict(Kg=5), dict(n_models=0), dict(n_models=33),
+    for bad in (dict(ld=50), dict(ld=62), dict(Kc=3), dict(Kg=5), dict(Kc=5000), dict(Kg=-1), dict(n_models=0), dict(n_models=33),
                 dict(mc_size=0), dict(n_layers=4), dict(n_cells=0), dict(event_offset=-1), dict(rows_per_cta=-1)):
         assert lib.brie_fit_create(C.byref(_desc(**bad)), C.byref(h)) < 0, bad
         assert len(lib.brie_last_error()) > 0
     d = _desc()
     d.xc_mask[0] = 2                      # bit beyond Kc
     assert lib.brie_fit_create(C.byref(d), C.byref(h)) < 0
+    # widths beyond the register-resident instantiations select the wide (GEMM) form: accepted, scratch grows
+    # by the prior-mean / residual planes and the Wc gradient
+    dw = _desc(Kc=24)
+    dw.xc_mask[0] = 0
+    dw.xc_width[0] = 24
+    assert lib.brie_fit_create(C.byref(dw), C.byref(h)) == 0
+    szw = _lib.FitSizes()
+    assert lib.brie_fit_get_sizes(h, C.byref(szw)) == 0
+    assert szw.scratch_bytes >= (2 * 100 * 64 + 24 * 64) * 4 and szw.n_col_tiles == 1
+    lib.brie_fit_destroy(h)
+    assert lib.brie_fit_create(C.byref(_desc(Kc=24, target=1)), C.byref(h)) < 0     # marginLik: narrow designs only
     # a caller-fixed rows_per_cta (gathered sub-fits keep their parent's) is honoured
     assert lib.brie_fit_create(C.byref(_desc(rows_per_cta=16)), C.byref(h)) == 0
     assert lib.brie_fit_get_sizes(h, C.byref(sz)) == 0 and sz.rows_per_cta == 16 and sz.n_row_chunks == 7
