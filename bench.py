@@ -408,14 +408,15 @@ def e2e_leg(ctx, name, min_iter, out_root):
     keys = ('isoform1', 'isoform2', 'ambiguous')[:c["layers"]]
     blocks = {k: [csc_matrix((Nc, lo), dtype=np.float32)] for k in keys}
     eff = np.ones((Ng, 6), np.float32)
-    for b, e0 in enumerate(range(lo, hi, 512)):
-        n = min(512, hi - e0)
-        sim = simulate_counts_device(Nc, n, design=c["design"], seed=100 + e0, with_efflen=c["eff"],
-                                     n_layers=c["layers"], pseudo_count=0.0, event_offset=e0, Xc=Xc, device=ctx.dev)
+    for b0 in range(lo // 512 * 512, hi, 512):             # global 512-event blocks: the data do not depend on the sharding
+        nb = min(512, Ng - b0)
+        sim = simulate_counts_device(Nc, nb, design=c["design"], seed=100 + b0, with_efflen=c["eff"],
+                                     n_layers=c["layers"], pseudo_count=0.0, event_offset=b0, Xc=Xc, device=ctx.dev)
+        s0, s1 = max(lo, b0) - b0, min(hi, b0 + nb) - b0        # this rank's columns of the block
         for k, t in zip(keys, sim['layers']):
-            blocks[k].append(device_block_to_csc(t, n))
+            blocks[k].append(device_block_to_csc(t[:, s0:s1], s1 - s0))
         if c["eff"]:
-            eff[e0:e0 + n] = sim['effLen']
+            eff[b0 + s0:b0 + s1] = sim['effLen'][s0:s1]
         del sim
     for k in keys:
         blocks[k].append(csc_matrix((Nc, Ng - hi), dtype=np.float32))

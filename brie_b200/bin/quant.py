@@ -107,7 +107,7 @@ def quant(in_file, cell_file=None, gene_file=None, out_file=None,
             intercept=intercept, intercept_mode=intercept_mode,
             min_iter=min_iter, max_iter=max_iter, MC_size=MC_size, batch_size=batch_size,
             pseudo_count=pseudo_count, base_mode=base_mode, tau_prior=tau_prior, seed=seed,
-            **(dict(out_dir=out_dir, resume=resume) if out_dir is not None else {}))
+            **(dict(out_dir=out_dir, resume=resume, out_keys=('Psi', 'Psi95CI', 'Z_std')) if out_dir is not None else {}))
 
     adata.uns['brie_version'] = brie_b200.__version__
     adata.uns['Xc_ids'] = Xc_ids

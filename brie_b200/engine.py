@@ -469,6 +469,9 @@ class FitEngine:
 
         t_ph = time.perf_counter()
         n_stage = int(min_iter / 6)
+        k_cap = int(os.environ.get("BRIE_KERNEL_TIMING", "0"))      # diagnostic: CUDA events around the first k_cap
+        if k_cap > 0:                                                # launches of the fused step kernel of this fit
+            self.kernel_timing(k_cap)
         if max(n_stage, add_iter) > self.trace_cap:
             raise ValueError("trace_cap %d too small for %d-step stages" % (self.trace_cap, max(n_stage, add_iter)))
         if do_init:
@@ -521,6 +524,13 @@ class FitEngine:
             self.losses.append(np.concatenate(parts) if parts else np.zeros(0, np.float32))
         self.loss_gene = self.eval_loss_gene(n_eval)                 # :261-264
         tick("fit.loss_gene", t_ph)
+        if k_cap > 0:
+            kms, kn = self.kernel_time_ms()
+            self.phase_s["step_kernel_ms_sum"] = kms
+            self.phase_s["step_kernel_launches"] = kn
+            # algorithmic bytes of one full-width launch: counts once + 48 B of state per model
+            self.phase_s["step_kernel_alg_bytes_sum"] = kn * float(self.Nc) * self.Ng * (4 * self.n_layers + 48 * self.M)
+            self.kernel_timing(0)
         return self.losses
 
     # ------------------------------------------------------------------ results

@@ -14,7 +14,7 @@ from scipy.stats import chi2
 
 from ..engine import FitEngine
 from ..sharding import event_shards
-from ..utils.layer_store import LayerStore
+from ..utils.layer_store import LayerStore, BIG_KEYS
 from ..settings import verbosity
 
 
@@ -124,7 +124,11 @@ def concate(BRIE_RV_list):
     return res_merge
 
 
-def _rv_from_engine(eng, m, Xc_model, Xg, intercept_mode):
+def _rv_from_engine(eng, m, Xc_model, Xg, intercept_mode, sink=None):
+    """Result container of model m.  The dense (cells, events) arrays Psi / Psi95CI / Z_std / Z_loc go to the host
+    through pinned staging (utils/d2h.py): into fresh arrays, or -- `sink` = (LayerStore, first event) -- straight
+    into their column range of the store's arrays / memory maps, leaving (cells, 0) stubs in the container."""
+    from ..utils import d2h
     rv = BRIE_RV()
     rv.Nc, rv.Ng = eng.Nc, eng.Ng
     rv.Kc, rv.Kg = len(eng.masks[m]), eng.Kg_real
@@ -134,8 +138,15 @@ def _rv_from_engine(eng, m, Xc_model, Xg, intercept_mode):
     rv.sigma, rv.intercept = p['sigma'], p['intercept']
     rv.cell_coeff, rv.gene_coeff = p['Wc_loc'], p['Wg_loc']
     Psi, CI, Zstd = eng.posterior(m)
-    rv.Psi, rv.Psi95CI, rv.Z_std = Psi.cpu().numpy(), CI.cpu().numpy(), Zstd.cpu().numpy()
-    rv.Z_loc = eng.Z_loc[m, :, :eng.Ng].cpu().numpy()
+    big = dict(Psi=Psi, Psi95CI=CI, Z_std=Zstd, Z_loc=eng.Z_loc[m, :, :eng.Ng])
+    for k, t in big.items():
+        if sink is None:
+            setattr(rv, k, d2h.to_host(t))
+        else:
+            store, e0 = sink
+            if k in store.arrays:
+                d2h.to_host_columns(t, store.arrays[k], e0)
+            setattr(rv, k, np.zeros((rv.Nc, 0), np.float32))
     rv.losses = eng.losses[m]
     rv.loss_gene = eng.loss_gene[m].cpu().numpy()
     rv.intercept_mode = intercept_mode
@@ -180,6 +191,7 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     MC_size = keyargs.pop('MC_size', 1)
     target = keyargs.pop('target', "ELBO")                          # reaches BRIE2.fit through **keyargs (:144)
     host_side_effect = keyargs.pop('host_side_effect', True)
+    out_sink = keyargs.pop('out_sink', None)                        # (LayerStore, first event): fitBRIE's output arrays
     for k in ('optimizer', 'learn_rate', 'verbose'):                # accepted and ignored (:214-237)
         keyargs.pop(k, None)
 
@@ -187,7 +199,7 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     import time
     import torch
     from .. import ingest
-    timing = {} if os.environ.get("BRIE_TIMING") else None         # phase wall times (diagnostic; syncs the device)
+    timing = {} if (os.environ.get("BRIE_TIMING") or os.environ.get("BRIE_KERNEL_TIMING")) else None         # phase wall times (diagnostic; syncs the device)
 
     def _tick(name, t0):
         if timing is not None:
@@ -287,7 +299,7 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
         for j, mid in enumerate(ids_e):
             n_iter_rows[mid] = eng.n_iter[j]
             if mid == 0:
-                brie_results = _rv_from_engine(eng, j, Xc[:, base_cols], Xg, intercept_mode)   # :146
+                brie_results = _rv_from_engine(eng, j, Xc[:, base_cols], Xg, intercept_mode, out_sink)   # :146
             else:
                 lg_tests[mid - 1] = eng.loss_gene[j].cpu().numpy()
                 if not full:
@@ -391,6 +403,8 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
     `out_dir` (not in the reference): directory for `.npy` memory maps of the dense
     (cells, events) outputs Psi / Psi95CI / Z_std / Z_loc, written event chunk by event chunk
     (and rank by rank) -- for fits whose outputs exceed host RAM; default: RAM arrays.
+    `out_keys` (not in the reference): which of ('Psi', 'Psi95CI', 'Z_std', 'Z_loc') to bring back from the
+    device (default all four; brie-quant with --outDir drops Z_loc, which AnnData never stores).
     `resume` (not in the reference; needs `out_dir`): every finished event chunk is checkpointed
     under `out_dir`; with resume=True a re-run of the same fit (same data shape, design, seed and
     schedule) skips the chunks already there and returns what the uninterrupted fit would have.
@@ -410,6 +424,7 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
     n_models = 1 + len(LRT_index)
     out_dir = keyargs.pop('out_dir', None)
     resume = keyargs.pop('resume', False)
+    out_keys = tuple(keyargs.pop('out_keys', None) or BIG_KEYS)
 
     dist, rank, world = _dist_info()
     if (Xg is None or Xg.shape[1] == 0) and intercept_mode.upper() != 'CELL':   # :241
@@ -424,7 +439,7 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
         # .npy memory maps under out_dir shared by all ranks) instead of np.append (:55-76)
         signature = _fit_signature(Nc, Ng, Xc, LRT_index, layer_keys, _n_gene, world, intercept, intercept_mode,
                                    pseudo_count, sigma, base_mode, keyargs) if out_dir is not None else None
-        store = LayerStore(Nc, Ng, out_dir, rank, world, dist, signature=signature, resume=resume)
+        store = LayerStore(Nc, Ng, out_dir, rank, world, dist, keys=out_keys, signature=signature, resume=resume)
         res_list = []
         for e0 in range(lo, hi, chunk):
             _done = store.load_chunk(e0, min(e0 + chunk, hi))
@@ -440,7 +455,7 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
                 intercept=intercept, intercept_mode=intercept_mode,
                 LRT_index=LRT_index, pseudo_count=pseudo_count, sigma=sigma,
                 base_mode=base_mode, tau_prior=tau_prior, group_size=_n_gene,
-                event_offset=e0, n_events_total=Ng, host_side_effect=False, **keyargs)
+                event_offset=e0, n_events_total=Ng, host_side_effect=False, out_sink=(store, e0), **keyargs)
             _t0 = time.perf_counter()
             store.put(e0, _ResVal)
             if getattr(_ResVal, 'timing', None) is not None:
@@ -460,7 +475,7 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
         # column range of the output arrays / memory maps; only per-event vectors are gathered.
         lo, hi = event_shards(Ng, world, 1)[rank]
         _idx = range(lo, hi)
-        store = LayerStore(Nc, Ng, out_dir, rank, world, dist)
+        store = LayerStore(Nc, Ng, out_dir, rank, world, dist, keys=out_keys)
         _count_layers = [adata.layers[_key][:, _idx] for _key in layer_keys]
         _effLen = adata.varm['effLen'][_idx, :] if 'effLen' in adata.varm else None
         local = fit_BRIE_matrix(
@@ -468,7 +483,7 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
             intercept_mode=intercept_mode, LRT_index=LRT_index,
             pseudo_count=pseudo_count, sigma=sigma, base_mode=base_mode,
             tau_prior=tau_prior, event_offset=lo, n_events_total=Ng,
-            dist_group=dist.group.WORLD, **keyargs)
+            dist_group=dist.group.WORLD, out_sink=(store, lo), **keyargs)
         store.put(lo, local, checkpoint=False)
         parts = [None] * world
         dist.all_gather_object(parts, local)

@@ -73,7 +73,9 @@ def dump_results(adata):
     cell_coeff by loop position rather than by LRT_index."""
     n_events = adata.shape[1]
     table = adata.var[['n_counts', 'n_counts_uniq']].astype(int)
-    table['cdr'] = np.asarray((adata.X > 0).mean(0)).reshape(-1)
+    # cell detection rate per event; a caller that no longer holds the counts may supply var['cdr']
+    table['cdr'] = (np.asarray(adata.var['cdr']) if 'cdr' in adata.var
+                    else np.asarray((adata.X > 0).mean(0)).reshape(-1))
     for key in ('intercept', 'sigma'):
         table[key] = adata.varm[key][:, 0] if key in adata.varm else [None] * n_events
     tested = adata.uns['brie_param']['LRT_index'] if 'brie_param' in adata.uns else []

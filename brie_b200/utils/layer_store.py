@@ -87,7 +87,9 @@ class LayerStore:
         (cells, 0) stubs behind, so BRIE_RV.concate only appends the per-event vectors."""
         e1 = e0 + result.Ng
         for k in self.keys:
-            self.arrays[k][:, e0:e1] = getattr(result, k)
+            v = getattr(result, k, None)
+            if v is not None and v.shape[1] == e1 - e0:      # not yet written through fit_BRIE_matrix's out_sink
+                self.arrays[k][:, e0:e1] = v
             setattr(result, k, np.zeros((self.shape[0], 0), np.float32))
         self.ranges.append((e0, e1))
         if self.out_dir is not None and checkpoint:   # big arrays on disk first, then the marker file

@@ -23,6 +23,10 @@ SHAPES = {
     "C4": dict(Nc=200000, Ng=4096, design='none', eff=False, layers=2, masks=[[]], mode='cell', Kg=8),
     "W16": dict(Nc=20000, Ng=4096, design='wide15', eff=False, layers=2, masks=[list(range(15))], mode='gene', Kg=0),
     "C5": dict(Nc=1000000, Ng=512, design='pseudotime', eff=True, layers=3, masks=[[0], []], mode='gene', Kg=0),
+    # wide designs (contractions as GEMMs around the fused kernel): 24 cell covariates; 20 gene features + cell intercept
+    "W24": dict(Nc=20000, Ng=4096, design='wide15', eff=False, layers=2, masks=[list(range(24))], mode='gene', Kg=0, Kc_extra=9),
+    "G20": dict(Nc=200000, Ng=2048, design='none', eff=False, layers=2, masks=[[]], mode='cell', Kg=20),
+    "K8G8": dict(Nc=50000, Ng=4096, design='wide15', eff=False, layers=2, masks=[list(range(8))], mode='gene', Kg=8),
 }
 
 
@@ -31,6 +35,9 @@ def run(name, steps=30, warm=5, loss=False):
     sim = simulate_counts_device(c['Nc'], c['Ng'], design=c['design'], seed=3, with_efflen=c['eff'], n_layers=c['layers'])
     nz = float(((sim['layers'][0] + sim['layers'][1] + (sim['layers'][2] if c['layers'] > 2 else 0)) > 0).float().mean())
     Xg = np.random.default_rng(0).standard_normal((c['Ng'], c['Kg'])).astype(np.float32) if c['Kg'] else None
+    if c.get('Kc_extra'):                     # more covariates than the synthetic design draws: standard-normal extras
+        sim['Xc'] = np.concatenate([sim['Xc'], np.random.default_rng(1).standard_normal(
+            (c['Nc'], c['Kc_extra'])).astype(np.float32)], axis=1)
     eng = FitEngine(sim['layers'], effLen=sim['effLen'], Xc=sim['Xc'], Xg=Xg, masks=c['masks'],
                     intercept_mode=c['mode'], MC_size=3, seed=1, n_events=c['Ng'], trace_cap=8,
                     group_size=max(1, -(-500000 // c['Nc'])))
@@ -52,7 +59,8 @@ def run(name, steps=30, warm=5, loss=False):
     kms, kn = eng.kernel_time_ms()
     M = len(c['masks'])
     alg = c['Nc'] * c['Ng'] * (4 * c['layers'] + 48 * M)
-    out = dict(shape=name, cells=c['Nc'], events=c['Ng'], models=M, Kc=eng.Kc_real, Kg=eng.Kg_real, mode=c['mode'],
+    step_alg = alg + (c['Nc'] * c['Ng'] * 16 * M if eng.wide else 0)      # wide: + prior-mean / residual planes, written and read
+    out = dict(shape=name, wide=bool(eng.wide), step_frac_of_measured_hbm=round(step_alg / (ms * 1e-3) / 1e9 / PEAK, 4), cells=c['Nc'], events=c['Ng'], models=M, Kc=eng.Kc_real, Kg=eng.Kg_real, mode=c['mode'],
                layers=c['layers'], loss_trace=loss, nonzero_fraction=round(nz, 4), ms_per_step=round(ms, 4),
                kernel_ms=round(kms / kn, 4), value=c['Nc'] * c['Ng'] * 3 * M / (ms * 1e-3),
                alg_GBps=round(alg / (kms / kn * 1e-3) / 1e9, 1), frac_of_measured_hbm=round(alg / (kms / kn * 1e-3) / 1e9 / PEAK, 4),
