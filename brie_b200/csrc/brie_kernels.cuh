@@ -122,6 +122,38 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- TMA-bulk form of the row ring (measurement variant, -DBRIE_RING_TMA=1; default: LDGSTS) ---------------------
+// One elected lane per warp issues one cp.async.bulk (global -> shared, completion on an mbarrier) per array and
+// row -- a TC * 4-byte contiguous segment -- instead of every lane issuing one 16-byte cp.async per array.
+// A/B on hardware: profiles/r2_ab_tma_ring.md.  The variant covers the dense column walk only (no active-block
+// list): a compacted tile is 16 separate 32-byte blocks per array, below the bulk copy's 16-byte granule economy.
+#ifndef BRIE_RING_TMA
+#define BRIE_RING_TMA 0
+#endif
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "BRIE_MBAR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra BRIE_MBAR_DONE;\n\t"
+      "bra BRIE_MBAR_WAIT;\n\t"
+      "BRIE_MBAR_DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // keras Adam update_step (TF 2.15): m += (g-m)(1-b1); v += (g^2-v)(1-b2);
 // x -= alpha_t * m / (sqrt(v) + eps)
 __device__ __forceinline__ void adam_update(float& x, float& m, float& v, float g, float alpha) {
@@ -478,7 +510,48 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   // zero-filled, they compute on zeros and store nothing, so a partly active tile only pays for the
   // 32-byte sectors that hold active events.
   const uint32_t rc_lane = (uint32_t)__cvta_generic_to_shared(s_rc) + lane * 4;
+#if BRIE_RING_TMA
+  __shared__ __align__(8) uint64_t s_bar[kWarps][kRingStages];
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[warp][0]);
+  // bytes of this tile's row segment inside ld (the last tile of a row may be partial; ld % 32 == 0)
+  const uint32_t seg_bytes = (uint32_t)min((int64_t)TC, a.ld - (int64_t)tile * TC) * 4u;
+  if (a.blk_ids != nullptr) __trap();             // measurement variant: dense column walk only
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (seg_bytes < (uint32_t)TC * 4u || !has_c3) {   // slots no bulk copy ever fills must read as zero counts / state
+    for (int i = lane; i < kRingStages * NRA * TC; i += 32) s_ring[i] = 0.f;
+  }
+  __syncwarp();
+  uint32_t ring_phase = 0;                        // bit s: parity the next wait on stage s expects
+  const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(s_ring);
+#endif
   auto issue_row = [&](int lr, int stage) {       // lr: row index within the CTA
+#if BRIE_RING_TMA
+    if (lr < n_rows && lane == 0) {
+      fence_proxy_async();                        // the warp's generic reads / writes of this stage (two rows ago) come first
+      const uint32_t bar = bar0 + stage * 8;
+      const uint32_t relw = (uint32_t)lr * ld32 + (uint32_t)tile * TC;
+      const uint32_t dstw = ring_base + stage * (NRA * TC * 4);
+      mbar_expect_tx(bar, seg_bytes * (8u + (has_c3 ? 1u : 0u) + (EXT ? 1u : 0u)));
+      bulk_g2s(dstw + 0 * TC * 4, bZl + relw, seg_bytes, bar);
+      bulk_g2s(dstw + 1 * TC * 4, bZs + relw, seg_bytes, bar);
+      bulk_g2s(dstw + 2 * TC * 4, bC0 + relw, seg_bytes, bar);
+      bulk_g2s(dstw + 3 * TC * 4, bC1 + relw, seg_bytes, bar);
+      if (has_c3) bulk_g2s(dstw + 4 * TC * 4, bC2 + relw, seg_bytes, bar);
+      bulk_g2s(dstw + 5 * TC * 4, bA0 + relw, seg_bytes, bar);
+      bulk_g2s(dstw + 6 * TC * 4, bA1 + relw, seg_bytes, bar);
+      bulk_g2s(dstw + 7 * TC * 4, bA2 + relw, seg_bytes, bar);
+      bulk_g2s(dstw + 8 * TC * 4, bA3 + relw, seg_bytes, bar);
+      if (EXT) bulk_g2s(dstw + 9 * TC * 4, bPM + relw, seg_bytes, bar);
+    }
+    const bool ok = false;
+    const uint32_t rel = 0u;
+    const uint32_t dst = ring_lane + stage * (NRA * TC * 4);
+    (void)ok; (void)rel; (void)dst;
+#else
     const bool ok = act != 0 && lr < n_rows;
     const uint32_t rel = ok ? (uint32_t)lr * ld32 + col32 : 0u;
     const uint32_t dst = ring_lane + stage * (NRA * TC * 4);
@@ -492,6 +565,7 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     cp_async_lane<EPL * 4>(dst + 7 * TC * 4, bA2 + rel, ok);
     cp_async_lane<EPL * 4>(dst + 8 * TC * 4, bA3 + rel, ok);
     if (EXT) cp_async_lane<EPL * 4>(dst + 9 * TC * 4, bPM + rel, ok);
+#endif
     if (NRC > 0) {
       // The row's warp-uniform constants ride in the same commit group, one float per lane.  (As plain
       // loads issued a row ahead they shared a scoreboard with the tile constants loaded before the loop,
@@ -553,8 +627,15 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   int stage = 0;
   for (int lr = warp; lr < n_rows; lr += kWarps, stage ^= 1) {
     const int64_t row = row_begin + lr;
+#if BRIE_RING_TMA
+    __syncwarp();                         // every lane is done with the other stage (phase B / C of the previous row)
+#endif
     issue_row(lr + kWarps, stage ^ 1);    // prefetch the next row (zero-size copies past the end)
     cp_async_wait<1>();                   // this row's group has landed
+#if BRIE_RING_TMA
+    mbar_wait(bar0 + stage * 8, (ring_phase >> stage) & 1u);
+    ring_phase ^= 1u << stage;
+#endif
     float xc[KC > 0 ? KC : 1], wg[KG > 0 ? KG : 1];
     float b_row = 0.f, tau_row = 0.f;
     __syncwarp();                         // other lanes read this lane's copies (row constants, Monte-Carlo items)

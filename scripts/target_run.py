@@ -154,6 +154,7 @@ def main():
         for k in keys:                          # the container of the synthetic input is not part of the measurement
             del ad.layers[k]
         ad.X = csc_matrix((Nc, Ng), dtype=np.float32)
+        os.makedirs(out_dir, exist_ok=True)        # (a single-process fit with shared parameters keeps its layers in RAM)
         out_file = os.path.join(out_dir, "brie_quant.npz")
         ad.write_npz(out_file)
         df = io_utils.dump_results(ad)
