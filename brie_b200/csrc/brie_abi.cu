@@ -381,7 +381,9 @@ int brie_fit_bind(brie_fit* fit, const brie_fit_buffers* b) {
     if (!fit->blas) {
       cublasStatus_t st = cublasCreate(&fit->blas);
       if (st != CUBLAS_STATUS_SUCCESS) return fail(BRIE_ERR_CUDA, "cublasCreate failed: %s", blas_status(st));
-      cublasSetMathMode(fit->blas, CUBLAS_PEDANTIC_MATH);   // plain fp32 FMA accumulation: no TF32, no split-K surprises
+      // fp32 in, fp32 accumulate: the default math mode never down-converts to TF32 on its own, and these skinny
+      // (K x Nc x Ng) products want cuBLAS's split-K heuristics (pedantic mode ran them 2-3x slower)
+      cublasSetMathMode(fit->blas, CUBLAS_DEFAULT_MATH);
     }
   }
   return BRIE_OK;

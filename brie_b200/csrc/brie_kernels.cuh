@@ -358,6 +358,18 @@ constexpr int kQueueFields = 1;   // tile column of the element; its data is rea
 constexpr int kRingArrays = 9;    // Z_loc, Z_std_log, c1, c2, c3, m_loc, v_loc, m_std, v_std
 constexpr int kRingStages = 2;
 __host__ __device__ constexpr int step_tile_cols(int KC, int KG = 0) { return 32 * step_epl(KC, KG); }
+// Rows a warp processes per loop iteration.  The 2-events-per-lane instantiations take two adjacent rows at a time:
+// their 64-event row holds ~10 elements with reads, a third of a warp, so the Monte-Carlo phase (Philox, Box-Muller,
+// S likelihood samples: ~200 instructions whatever the number of items) ran mostly idle; the items of two rows
+// share one pass.  Ring stages, queue and per-lane state then match the 4-events-per-lane kernels byte for byte.
+// (16 covariates together with gene features keep one row per iteration: two rows' state next to 32 per-event and
+// up to 10 per-cell accumulators would spill.)
+#ifndef BRIE_FORCE_RPI1
+#define BRIE_FORCE_RPI1 0   // A/B aid (scripts/ab.sh): 1 = one row per iteration everywhere
+#endif
+__host__ __device__ constexpr int step_rpi(int KC, int KG = 0) {
+  return (!BRIE_FORCE_RPI1 && step_epl(KC, KG) == 2 && !(KC > 8 && KG > 0)) ? 2 : 1;
+}
 // Per-event constants of a column tile (Wc rows, Xg columns, intercept, sigma_log, 1/sigma^2) stay in
 // registers for narrow designs; wider ones (Kc + Kg >= 3) keep them in shared memory and re-read them
 // every row, so they are not live across the Monte-Carlo phase (no spills).  A/B on one box
@@ -376,16 +388,17 @@ __host__ __device__ constexpr int step_n_consts(int KC, int KG, bool CELL, bool 
 }
 constexpr int kRowConstSlots = 32;   // per warp and ring stage: Xc[c, :], Wg[c, :], per-cell intercept / sigma_log of the row
 __host__ __device__ constexpr int step_smem_bytes(int KC, int KG, bool CELL, bool LOSS, bool EXT = false) {
-  return (kWarps * kRingStages * (kRingArrays + (EXT ? 1 : 0)) + kWarps * kQueueFields + 7 +
+  return ((kWarps * kRingStages * (kRingArrays + (EXT ? 1 : 0)) + kWarps * kQueueFields) * step_rpi(KC, KG) + 7 +
           step_n_consts(KC, KG, CELL, LOSS)) *
              step_tile_cols(KC, KG) * 4 +
-         kWarps * kRingStages * kRowConstSlots * 4;
+         kWarps * kRingStages * step_rpi(KC, KG) * kRowConstSlots * 4;
 }
 
 template <int KC, int KG, bool CELL, bool LOSS, bool EXT = false>
 __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(const StepArgs a) {
   static_assert(!EXT || (KC == 0 && KG == 0), "the wide-design form takes all covariates through PM / R");
-  constexpr int NRA = kRingArrays + (EXT ? 1 : 0);   // ring arrays per stage (EXT: + the prior-mean tile)
+  constexpr int NRA = kRingArrays + (EXT ? 1 : 0);   // ring arrays per row slot (EXT: + the prior-mean tile)
+  constexpr int RPI = step_rpi(KC, KG);              // rows per loop iteration = row slots per ring stage
   using T = StepTraits<KC, KG, CELL, LOSS>;
   constexpr int NEV = T::NEV;
   constexpr int NCELL = T::NCELL;
@@ -424,11 +437,12 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     for (int j = 0; j < EPL; ++j) act |= (a.active[(int64_t)m * a.ld + g0 + j] != 0 ? 1u : 0u) << j;
   }
   extern __shared__ __align__(128) float smem[];
-  float* s_ring = smem + warp * (kRingStages * NRA * TC);
-  uint32_t* q = reinterpret_cast<uint32_t*>(smem + kWarps * kRingStages * NRA * TC +
-                                            warp * kQueueFields * TC);
-  float(*s_L)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * NRA * TC +
-                                                   kWarps * kQueueFields * TC);
+  constexpr int SLOT = NRA * TC;                     // floats of one row slot
+  float* s_ring = smem + warp * (kRingStages * RPI * SLOT);
+  uint32_t* q = reinterpret_cast<uint32_t*>(smem + kWarps * kRingStages * RPI * SLOT +
+                                            warp * kQueueFields * RPI * TC);
+  float(*s_L)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * RPI * SLOT +
+                                                   kWarps * kQueueFields * RPI * TC);
   uint32_t* s_ev = reinterpret_cast<uint32_t*>(s_L + 6);   // global event id of each tile column (RNG counter word)
   float(*s_k)[TC] = s_L + 7;                // kSm: rows Wc[0..KC), Xg[0..KG), then (gene mode) b, tau, 1/sigma^2
   // Gene-feature slots are stored XOR-permuted per lane (slot i of lane L holds feature i ^ pk(L), pk = the top
@@ -441,9 +455,9 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   for (int t = 0; t < KGB; ++t) pk |= ((lane >> (4 - t)) & 1) << (KGB - 1 - t);
   constexpr int NRC = KC + KG + (CELL ? 2 : 0);   // per-row (cell) constants: Xc[c, :], Wg[c, :], b[c], tau[c]
   static_assert(NRC <= kRowConstSlots, "row constants must fit one slot per lane");
-  float* s_rc = smem + (kWarps * kRingStages * NRA + kWarps * kQueueFields + 7 +
+  float* s_rc = smem + ((kWarps * kRingStages * NRA + kWarps * kQueueFields) * RPI + 7 +
                         step_n_consts(KC, KG, CELL, LOSS)) * TC +
-                warp * (kRingStages * kRowConstSlots);
+                warp * (kRingStages * RPI * kRowConstSlots);
 
   // Per-event constants of the tile go to shared memory before the barrier that decides whether the tile has
   // any active event: their loads overlap the `active` loads and that barrier also publishes them.
@@ -522,66 +536,70 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (seg_bytes < (uint32_t)TC * 4u || !has_c3) {   // slots no bulk copy ever fills must read as zero counts / state
-    for (int i = lane; i < kRingStages * NRA * TC; i += 32) s_ring[i] = 0.f;
+    for (int i = lane; i < kRingStages * RPI * SLOT; i += 32) s_ring[i] = 0.f;
   }
   __syncwarp();
   uint32_t ring_phase = 0;                        // bit s: parity the next wait on stage s expects
   const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(s_ring);
 #endif
-  auto issue_row = [&](int lr, int stage) {       // lr: row index within the CTA
+  auto issue_rows = [&](int lrb, int stage) {     // lrb: first of the RPI adjacent rows (index within the CTA)
 #if BRIE_RING_TMA
-    if (lr < n_rows && lane == 0) {
-      fence_proxy_async();                        // the warp's generic reads / writes of this stage (two rows ago) come first
+    if (lrb < n_rows && lane == 0) {
+      fence_proxy_async();                        // the warp's generic reads / writes of this stage (two iterations ago) come first
       const uint32_t bar = bar0 + stage * 8;
-      const uint32_t relw = (uint32_t)lr * ld32 + (uint32_t)tile * TC;
-      const uint32_t dstw = ring_base + stage * (NRA * TC * 4);
-      mbar_expect_tx(bar, seg_bytes * (8u + (has_c3 ? 1u : 0u) + (EXT ? 1u : 0u)));
-      bulk_g2s(dstw + 0 * TC * 4, bZl + relw, seg_bytes, bar);
-      bulk_g2s(dstw + 1 * TC * 4, bZs + relw, seg_bytes, bar);
-      bulk_g2s(dstw + 2 * TC * 4, bC0 + relw, seg_bytes, bar);
-      bulk_g2s(dstw + 3 * TC * 4, bC1 + relw, seg_bytes, bar);
-      if (has_c3) bulk_g2s(dstw + 4 * TC * 4, bC2 + relw, seg_bytes, bar);
-      bulk_g2s(dstw + 5 * TC * 4, bA0 + relw, seg_bytes, bar);
-      bulk_g2s(dstw + 6 * TC * 4, bA1 + relw, seg_bytes, bar);
-      bulk_g2s(dstw + 7 * TC * 4, bA2 + relw, seg_bytes, bar);
-      bulk_g2s(dstw + 8 * TC * 4, bA3 + relw, seg_bytes, bar);
-      if (EXT) bulk_g2s(dstw + 9 * TC * 4, bPM + relw, seg_bytes, bar);
+      const int nr = min(RPI, n_rows - lrb);
+      mbar_expect_tx(bar, seg_bytes * (8u + (has_c3 ? 1u : 0u) + (EXT ? 1u : 0u)) * (uint32_t)nr);
+      for (int r = 0; r < nr; ++r) {
+        const uint32_t relw = (uint32_t)(lrb + r) * ld32 + (uint32_t)tile * TC;
+        const uint32_t dstw = ring_base + (stage * RPI + r) * (SLOT * 4);
+        bulk_g2s(dstw + 0 * TC * 4, bZl + relw, seg_bytes, bar);
+        bulk_g2s(dstw + 1 * TC * 4, bZs + relw, seg_bytes, bar);
+        bulk_g2s(dstw + 2 * TC * 4, bC0 + relw, seg_bytes, bar);
+        bulk_g2s(dstw + 3 * TC * 4, bC1 + relw, seg_bytes, bar);
+        if (has_c3) bulk_g2s(dstw + 4 * TC * 4, bC2 + relw, seg_bytes, bar);
+        bulk_g2s(dstw + 5 * TC * 4, bA0 + relw, seg_bytes, bar);
+        bulk_g2s(dstw + 6 * TC * 4, bA1 + relw, seg_bytes, bar);
+        bulk_g2s(dstw + 7 * TC * 4, bA2 + relw, seg_bytes, bar);
+        bulk_g2s(dstw + 8 * TC * 4, bA3 + relw, seg_bytes, bar);
+        if (EXT) bulk_g2s(dstw + 9 * TC * 4, bPM + relw, seg_bytes, bar);
+      }
     }
-    const bool ok = false;
-    const uint32_t rel = 0u;
-    const uint32_t dst = ring_lane + stage * (NRA * TC * 4);
-    (void)ok; (void)rel; (void)dst;
-#else
-    const bool ok = act != 0 && lr < n_rows;
-    const uint32_t rel = ok ? (uint32_t)lr * ld32 + col32 : 0u;
-    const uint32_t dst = ring_lane + stage * (NRA * TC * 4);
-    cp_async_lane<EPL * 4>(dst + 0 * TC * 4, bZl + rel, ok);
-    cp_async_lane<EPL * 4>(dst + 1 * TC * 4, bZs + rel, ok);
-    cp_async_lane<EPL * 4>(dst + 2 * TC * 4, bC0 + rel, ok);
-    cp_async_lane<EPL * 4>(dst + 3 * TC * 4, bC1 + rel, ok);
-    cp_async_lane<EPL * 4>(dst + 4 * TC * 4, bC2 + (has_c3 ? rel : 0u), ok && has_c3);
-    cp_async_lane<EPL * 4>(dst + 5 * TC * 4, bA0 + rel, ok);
-    cp_async_lane<EPL * 4>(dst + 6 * TC * 4, bA1 + rel, ok);
-    cp_async_lane<EPL * 4>(dst + 7 * TC * 4, bA2 + rel, ok);
-    cp_async_lane<EPL * 4>(dst + 8 * TC * 4, bA3 + rel, ok);
-    if (EXT) cp_async_lane<EPL * 4>(dst + 9 * TC * 4, bPM + rel, ok);
 #endif
-    if (NRC > 0) {
-      // The row's warp-uniform constants ride in the same commit group, one float per lane.  (As plain
-      // loads issued a row ahead they shared a scoreboard with the tile constants loaded before the loop,
-      // and the first use of those waited for the prefetch every row: 23 % of the stall samples.)
-      const bool okc = lane < NRC && lr < n_rows;
-      const uint32_t r = okc ? (uint32_t)lr : 0u;
-      const float* src = a.Xc;
-      if (lane < KC) src = a.Xc + cell0 * KC + (r * KC + lane);
-      else if (lane < KC + KG) src = a.Wg + cell0 * KG + (r * KG + (lane - KC));
-      else if (CELL && lane == KC + KG) src = a.b + cell0 + r;
-      else if (CELL) src = a.tau + cell0 + r;
-      cp_async_lane<4>(rc_lane + stage * (kRowConstSlots * 4), src, okc);
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+      const int lr = lrb + r;
+#if !BRIE_RING_TMA
+      const bool ok = act != 0 && lr < n_rows;
+      const uint32_t rel = ok ? (uint32_t)lr * ld32 + col32 : 0u;
+      const uint32_t dst = ring_lane + (stage * RPI + r) * (SLOT * 4);
+      cp_async_lane<EPL * 4>(dst + 0 * TC * 4, bZl + rel, ok);
+      cp_async_lane<EPL * 4>(dst + 1 * TC * 4, bZs + rel, ok);
+      cp_async_lane<EPL * 4>(dst + 2 * TC * 4, bC0 + rel, ok);
+      cp_async_lane<EPL * 4>(dst + 3 * TC * 4, bC1 + rel, ok);
+      cp_async_lane<EPL * 4>(dst + 4 * TC * 4, bC2 + (has_c3 ? rel : 0u), ok && has_c3);
+      cp_async_lane<EPL * 4>(dst + 5 * TC * 4, bA0 + rel, ok);
+      cp_async_lane<EPL * 4>(dst + 6 * TC * 4, bA1 + rel, ok);
+      cp_async_lane<EPL * 4>(dst + 7 * TC * 4, bA2 + rel, ok);
+      cp_async_lane<EPL * 4>(dst + 8 * TC * 4, bA3 + rel, ok);
+      if (EXT) cp_async_lane<EPL * 4>(dst + 9 * TC * 4, bPM + rel, ok);
+#endif
+      if (NRC > 0) {
+        // The row's warp-uniform constants ride in the same commit group, one float per lane.  (As plain
+        // loads issued a row ahead they shared a scoreboard with the tile constants loaded before the loop,
+        // and the first use of those waited for the prefetch every row: 23 % of the stall samples.)
+        const bool okc = lane < NRC && lr < n_rows;
+        const uint32_t rr = okc ? (uint32_t)lr : 0u;
+        const float* src = a.Xc;
+        if (lane < KC) src = a.Xc + cell0 * KC + (rr * KC + lane);
+        else if (lane < KC + KG) src = a.Wg + cell0 * KG + (rr * KG + (lane - KC));
+        else if (CELL && lane == KC + KG) src = a.b + cell0 + rr;
+        else if (CELL) src = a.tau + cell0 + rr;
+        cp_async_lane<4>(rc_lane + (stage * RPI + r) * (kRowConstSlots * 4), src, okc);
+      }
     }
-    cp_async_commit();
+    cp_async_commit();                            // one group per iteration
   };
-  issue_row(warp, 0);
+  issue_rows(warp * RPI, 0);
 
   float wc[KC > 0 ? KC : 1][EPL];
   float xg[KG > 0 ? KG : 1][EPL];
@@ -624,193 +642,230 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
   const uint32_t stream0 = brie_stream_word(BRIE_PHASE_TRAIN, (uint32_t)a.model_id[m], 0u);
   const uint32_t lt_mask = (1u << lane) - 1u;
 
+  // per-cell sums of one row over the 32 lanes -> one partial per column tile
+  auto cell_reduce_store = [&](float (&cacc)[NCELL > 0 ? NCELL : 1], int64_t row) {
+    float* pc = a.part_cell + (((int64_t)tile * a.M + m) * a.Nc + row) * NCELL;
+    if (KG > 0) {
+      // Halving butterfly: slot i of this lane holds feature i ^ pk, so at every step all lanes keep
+      // the lower half of their slots and hand the upper half to the partner that keeps those features
+      // (no selects); KG - 1 + log2(32 / KG) shuffles instead of 5 KG.
+#pragma unroll
+      for (int t = 0; t < KGB; ++t) {
+        const int H = KG >> (t + 1);
+#pragma unroll
+        for (int i = 0; i < H; ++i) cacc[i] += __shfl_xor_sync(0xffffffffu, cacc[H + i], 16 >> t);
+      }
+      float sum = cacc[0];
+#pragma unroll
+      for (int o = 16 >> KGB; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if ((lane & ((32 >> KGB) - 1)) == 0) pc[pk] = sum;
+    }
+    if (CELL) {  // d/d intercept and d/d sigma_log of the cell: two values, one per half-warp after the first step
+      const bool hi = (lane & 16) != 0;
+      const float keep = hi ? cacc[KG + 1] : cacc[KG], send = hi ? cacc[KG] : cacc[KG + 1];
+      float sum = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if ((lane & 15) == 0) pc[KG + (hi ? 1 : 0)] = sum;
+    }
+  };
+
   int stage = 0;
-  for (int lr = warp; lr < n_rows; lr += kWarps, stage ^= 1) {
-    const int64_t row = row_begin + lr;
+  for (int lrb = warp * RPI; lrb < n_rows; lrb += kWarps * RPI, stage ^= 1) {
 #if BRIE_RING_TMA
-    __syncwarp();                         // every lane is done with the other stage (phase B / C of the previous row)
+    __syncwarp();                         // every lane is done with the other stage (phase B / C of the previous iteration)
 #endif
-    issue_row(lr + kWarps, stage ^ 1);    // prefetch the next row (zero-size copies past the end)
-    cp_async_wait<1>();                   // this row's group has landed
+    issue_rows(lrb + kWarps * RPI, stage ^ 1);   // prefetch the next rows (zero-size copies past the end)
+    cp_async_wait<1>();                   // this iteration's group has landed
 #if BRIE_RING_TMA
     mbar_wait(bar0 + stage * 8, (ring_phase >> stage) & 1u);
     ring_phase ^= 1u << stage;
 #endif
-    float xc[KC > 0 ? KC : 1], wg[KG > 0 ? KG : 1];
-    float b_row = 0.f, tau_row = 0.f;
     __syncwarp();                         // other lanes read this lane's copies (row constants, Monte-Carlo items)
-    if (NRC > 0) {
-      const float* rc = s_rc + stage * kRowConstSlots;
-#pragma unroll
-      for (int k = 0; k < KC; ++k) xc[k] = rc[k];
-#pragma unroll
-      for (int k = 0; k < KG; ++k) wg[k] = rc[KC + (k ^ pk)];
-      if (CELL) { b_row = rc[KC + KG]; tau_row = rc[KC + KG + 1]; }
-      __syncwarp();                       // all lanes have read them before any lane's next prefetch overwrites the slot two rows on
-    }
-    const Vec* st = reinterpret_cast<const Vec*>(s_ring + stage * (NRA * TC)) + lane;
-    float mu[EPL], lam[EPL], c1[EPL], c2[EPL], c3[EPL], pmx[EPL];
-#pragma unroll
-    for (int j = 0; j < EPL; ++j) pmx[j] = 0.f;
-    if (EXT) vec_get<EPL>(st[9 * 32], pmx);
-    vec_get<EPL>(st[0 * 32], mu);
-    vec_get<EPL>(st[1 * 32], lam);
-    vec_get<EPL>(st[2 * 32], c1);
-    vec_get<EPL>(st[3 * 32], c2);
-    vec_get<EPL>(st[4 * 32], c3);
-    float is2_row = 1.f;
-    if (CELL) is2_row = fast_exp(-2.0f * tau_row);
-    float cacc[NCELL > 0 ? NCELL : 1];
-#pragma unroll
-    for (int i = 0; i < (NCELL > 0 ? NCELL : 1); ++i) cacc[i] = 0.f;
+    float* const rs0 = s_ring + stage * (RPI * SLOT);                 // row slot r of this stage: rs0 + r * SLOT
+    float mu[RPI][EPL], lam[RPI][EPL], gmu[RPI][EPL], glam[RPI][EPL];
+    float cacc1[NCELL > 0 ? NCELL : 1];   // RPI == 1: kept until after phase C (as tuned for the gene-feature kernels)
+    uint32_t nz = 0;                      // bit r * EPL + j: element j of row r has reads
 
     // ---- phase A: KL terms, shared-parameter accumulators, non-zero detection ----
-    if (kSm) {  // this row's copy of the tile constants (dead again before the Monte-Carlo phase)
 #pragma unroll
-      for (int k = 0; k < KC; ++k) vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[k][lane * EPL]), wc[k]);
+    for (int r = 0; r < RPI; ++r) {
+      const int lr = lrb + r;
+      const Vec* st = reinterpret_cast<const Vec*>(rs0 + r * SLOT) + lane;
+      float xc[KC > 0 ? KC : 1], wg[KG > 0 ? KG : 1];
+      float b_row = 0.f, tau_row = 0.f;
+      if (NRC > 0) {
+        const float* rc = s_rc + (stage * RPI + r) * kRowConstSlots;
 #pragma unroll
-      for (int k = 0; k < KG; ++k)
-        vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + (k ^ pk)][lane * EPL]), xg[k]);
-      if (!CELL) {
-        vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + KG][lane * EPL]), bb);
-        vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + KG + 1][lane * EPL]), tau);
-        vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + KG + 2][lane * EPL]), is2);
+        for (int k = 0; k < KC; ++k) xc[k] = rc[k];
+#pragma unroll
+        for (int k = 0; k < KG; ++k) wg[k] = rc[KC + (k ^ pk)];
+        if (CELL) { b_row = rc[KC + KG]; tau_row = rc[KC + KG + 1]; }
+        if (RPI == 1) __syncwarp();       // all lanes have read them before any lane's next prefetch overwrites the slot two iterations on
       }
-    }
-    float gmu[EPL], glam[EPL];
-    uint32_t nz = 0;
-#if BRIE_F32X2
-    static_assert(EPL % 2 == 0, "packed pairs need an even number of events per lane");
-    float2 cacc2[NCELL > 0 ? NCELL : 1];
+      float c1[EPL], c2[EPL], c3[EPL], pmx[EPL];
 #pragma unroll
-    for (int i = 0; i < (NCELL > 0 ? NCELL : 1); ++i) cacc2[i] = make_float2(0.f, 0.f);
+      for (int j = 0; j < EPL; ++j) pmx[j] = 0.f;
+      if (EXT) vec_get<EPL>(st[9 * 32], pmx);
+      vec_get<EPL>(st[0 * 32], mu[r]);
+      vec_get<EPL>(st[1 * 32], lam[r]);
+      vec_get<EPL>(st[2 * 32], c1);
+      vec_get<EPL>(st[3 * 32], c2);
+      vec_get<EPL>(st[4 * 32], c3);
+      float is2_row = 1.f;
+      if (CELL) is2_row = fast_exp(-2.0f * tau_row);
+      float caccr[NCELL > 0 ? NCELL : 1];
+      float (&cacc)[NCELL > 0 ? NCELL : 1] = RPI == 1 ? cacc1 : caccr;
 #pragma unroll
-    for (int p = 0; p < EPL / 2; ++p) {
-      const int j0 = 2 * p, j1 = 2 * p + 1;
-      const float2 tj = CELL ? f2_splat(tau_row) : make_float2(tau[j0], tau[j1]);
-      const float2 i2 = CELL ? f2_splat(is2_row) : make_float2(is2[j0], is2[j1]);
-      float2 pm = CELL ? f2_splat(b_row) : make_float2(bb[j0], bb[j1]);
-      if (EXT) pm = f2_add(pm, make_float2(pmx[j0], pmx[j1]));
+      for (int i = 0; i < (NCELL > 0 ? NCELL : 1); ++i) cacc[i] = 0.f;
+      if (kSm) {  // this row's copy of the tile constants (dead again before the Monte-Carlo phase)
 #pragma unroll
-      for (int k = 0; k < KC; ++k) pm = f2_fma(f2_splat(xc[k]), make_float2(wc[k][j0], wc[k][j1]), pm);
+        for (int k = 0; k < KC; ++k) vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[k][lane * EPL]), wc[k]);
 #pragma unroll
-      for (int k = 0; k < KG; ++k) pm = f2_fma(f2_splat(wg[k]), make_float2(xg[k][j0], xg[k][j1]), pm);
-      const float2 d = f2_sub(make_float2(lam[j0], lam[j1]), tj);
-      const float2 dd = f2_mul(d, f2_splat(2.0f * kLog2e));
-      const float2 e2 = make_float2(ex2_approx(dd.x), ex2_approx(dd.y));   // s^2 / sigma^2
-      const float2 diff = f2_sub(make_float2(mu[j0], mu[j1]), pm);
-      const float2 r = f2_mul(diff, i2);                                   // (mu - m) / sigma^2
-      const float2 q2 = f2_mul(diff, r);                                   // ((mu - m) / sigma)^2
-      const float2 nr = make_float2(-r.x, -r.y);
-      const float2 e2m1 = f2_add(e2, f2_splat(-1.0f));
-      gmu[j0] = r.x; gmu[j1] = r.y;
-      glam[j0] = e2m1.x; glam[j1] = e2m1.y;
-      if (c1[j0] + c2[j0] + c3[j0] > 0.f) nz |= 1u << j0;
-      if (c1[j1] + c2[j1] + c3[j1] > 0.f) nz |= 1u << j1;
-      const float2 gt = f2_sub(f2_sub(f2_splat(1.0f), q2), e2);            // d loss / d sigma_log
-#pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        const float2 t = f2_fma(f2_splat(xc[k]), nr, make_float2(acc[k][j0], acc[k][j1]));
-        acc[k][j0] = t.x; acc[k][j1] = t.y;
-      }
-      if (!CELL) {
-        const float2 t = f2_sub(make_float2(acc[T::kGB][j0], acc[T::kGB][j1]), r);
-        acc[T::kGB][j0] = t.x; acc[T::kGB][j1] = t.y;
-        const float2 u = f2_add(make_float2(acc[T::kGT][j0], acc[T::kGT][j1]), gt);
-        acc[T::kGT][j0] = u.x; acc[T::kGT][j1] = u.y;
-      }
-      if (LOSS) {                                                          // TFP _kl_normal_normal
-        const float2 kl = f2_sub(f2_fma(f2_splat(0.5f), q2, f2_mul(f2_splat(0.5f), e2m1)), d);
-        const float2 t = f2_add(make_float2(acc[T::kLoss][j0], acc[T::kLoss][j1]), kl);
-        acc[T::kLoss][j0] = t.x; acc[T::kLoss][j1] = t.y;
-      }
-      if (NCELL > 0) {
-        const float2 nrm = make_float2((g0 + j0) < a.Ng ? nr.x : 0.f, (g0 + j1) < a.Ng ? nr.y : 0.f);
-#pragma unroll
-        for (int k = 0; k < KG; ++k) cacc2[k] = f2_fma(make_float2(xg[k][j0], xg[k][j1]), nrm, cacc2[k]);
-        if (CELL) {
-          const float2 gm = make_float2((g0 + j0) < a.Ng ? gt.x : 0.f, (g0 + j1) < a.Ng ? gt.y : 0.f);
-          cacc2[KG] = f2_add(cacc2[KG], nrm);
-          cacc2[KG + 1] = f2_add(cacc2[KG + 1], gm);
+        for (int k = 0; k < KG; ++k)
+          vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + (k ^ pk)][lane * EPL]), xg[k]);
+        if (!CELL) {
+          vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + KG][lane * EPL]), bb);
+          vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + KG + 1][lane * EPL]), tau);
+          vec_get<EPL>(*reinterpret_cast<const Vec*>(&s_k[KC + KG + 2][lane * EPL]), is2);
         }
       }
-    }
+#if BRIE_F32X2
+      static_assert(EPL % 2 == 0, "packed pairs need an even number of events per lane");
+      float2 cacc2[NCELL > 0 ? NCELL : 1];
 #pragma unroll
-    for (int i = 0; i < NCELL; ++i) cacc[i] = cacc2[i].x + cacc2[i].y;
+      for (int i = 0; i < (NCELL > 0 ? NCELL : 1); ++i) cacc2[i] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < EPL / 2; ++p) {
+        const int j0 = 2 * p, j1 = 2 * p + 1;
+        const float2 tj = CELL ? f2_splat(tau_row) : make_float2(tau[j0], tau[j1]);
+        const float2 i2 = CELL ? f2_splat(is2_row) : make_float2(is2[j0], is2[j1]);
+        float2 pm = CELL ? f2_splat(b_row) : make_float2(bb[j0], bb[j1]);
+        if (EXT) pm = f2_add(pm, make_float2(pmx[j0], pmx[j1]));
+#pragma unroll
+        for (int k = 0; k < KC; ++k) pm = f2_fma(f2_splat(xc[k]), make_float2(wc[k][j0], wc[k][j1]), pm);
+#pragma unroll
+        for (int k = 0; k < KG; ++k) pm = f2_fma(f2_splat(wg[k]), make_float2(xg[k][j0], xg[k][j1]), pm);
+        const float2 d = f2_sub(make_float2(lam[r][j0], lam[r][j1]), tj);
+        const float2 dd = f2_mul(d, f2_splat(2.0f * kLog2e));
+        const float2 e2 = make_float2(ex2_approx(dd.x), ex2_approx(dd.y));   // s^2 / sigma^2
+        const float2 diff = f2_sub(make_float2(mu[r][j0], mu[r][j1]), pm);
+        const float2 rr = f2_mul(diff, i2);                                  // (mu - m) / sigma^2
+        const float2 q2 = f2_mul(diff, rr);                                  // ((mu - m) / sigma)^2
+        const float2 nr = make_float2(-rr.x, -rr.y);
+        const float2 e2m1 = f2_add(e2, f2_splat(-1.0f));
+        gmu[r][j0] = rr.x; gmu[r][j1] = rr.y;
+        glam[r][j0] = e2m1.x; glam[r][j1] = e2m1.y;
+        if (c1[j0] + c2[j0] + c3[j0] > 0.f) nz |= 1u << (r * EPL + j0);
+        if (c1[j1] + c2[j1] + c3[j1] > 0.f) nz |= 1u << (r * EPL + j1);
+        const float2 gt = f2_sub(f2_sub(f2_splat(1.0f), q2), e2);            // d loss / d sigma_log
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          const float2 t = f2_fma(f2_splat(xc[k]), nr, make_float2(acc[k][j0], acc[k][j1]));
+          acc[k][j0] = t.x; acc[k][j1] = t.y;
+        }
+        if (!CELL) {
+          const float2 t = f2_sub(make_float2(acc[T::kGB][j0], acc[T::kGB][j1]), rr);
+          acc[T::kGB][j0] = t.x; acc[T::kGB][j1] = t.y;
+          const float2 u = f2_add(make_float2(acc[T::kGT][j0], acc[T::kGT][j1]), gt);
+          acc[T::kGT][j0] = u.x; acc[T::kGT][j1] = u.y;
+        }
+        if (LOSS) {                                                          // TFP _kl_normal_normal
+          const float2 kl = f2_sub(f2_fma(f2_splat(0.5f), q2, f2_mul(f2_splat(0.5f), e2m1)), d);
+          const float2 t = f2_add(make_float2(acc[T::kLoss][j0], acc[T::kLoss][j1]), kl);
+          acc[T::kLoss][j0] = t.x; acc[T::kLoss][j1] = t.y;
+        }
+        if (NCELL > 0) {
+          const float2 nrm = make_float2((g0 + j0) < a.Ng ? nr.x : 0.f, (g0 + j1) < a.Ng ? nr.y : 0.f);
+#pragma unroll
+          for (int k = 0; k < KG; ++k) cacc2[k] = f2_fma(make_float2(xg[k][j0], xg[k][j1]), nrm, cacc2[k]);
+          if (CELL) {
+            const float2 gm = make_float2((g0 + j0) < a.Ng ? gt.x : 0.f, (g0 + j1) < a.Ng ? gt.y : 0.f);
+            cacc2[KG] = f2_add(cacc2[KG], nrm);
+            cacc2[KG + 1] = f2_add(cacc2[KG + 1], gm);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NCELL; ++i) cacc[i] = cacc2[i].x + cacc2[i].y;
 #else
 #pragma unroll
-    for (int j = 0; j < EPL; ++j) {
-      const float tj = CELL ? tau_row : tau[j];
-      const float i2 = CELL ? is2_row : is2[j];
-      float pm = CELL ? b_row : bb[j];
-      if (EXT) pm += pmx[j];
+      for (int j = 0; j < EPL; ++j) {
+        const float tj = CELL ? tau_row : tau[j];
+        const float i2 = CELL ? is2_row : is2[j];
+        float pm = CELL ? b_row : bb[j];
+        if (EXT) pm += pmx[j];
 #pragma unroll
-      for (int k = 0; k < KC; ++k) pm = fmaf(xc[k], wc[k][j], pm);
+        for (int k = 0; k < KC; ++k) pm = fmaf(xc[k], wc[k][j], pm);
 #pragma unroll
-      for (int k = 0; k < KG; ++k) pm = fmaf(wg[k], xg[k][j], pm);
-      const float d = lam[j] - tj;
-      const float e2 = ex2_approx((2.0f * kLog2e) * d);  // s^2 / sigma^2
-      const float diff = mu[j] - pm;
-      const float r = diff * i2;                         // (mu - m) / sigma^2
-      const float q2 = diff * r;                         // ((mu - m) / sigma)^2
-      gmu[j] = r;
-      glam[j] = e2 - 1.0f;
-      if (c1[j] + c2[j] + c3[j] > 0.f) nz |= 1u << j;
-      const float gt = 1.0f - q2 - e2;                   // d loss / d sigma_log
+        for (int k = 0; k < KG; ++k) pm = fmaf(wg[k], xg[k][j], pm);
+        const float d = lam[r][j] - tj;
+        const float e2 = ex2_approx((2.0f * kLog2e) * d);  // s^2 / sigma^2
+        const float diff = mu[r][j] - pm;
+        const float rr = diff * i2;                        // (mu - m) / sigma^2
+        const float q2 = diff * rr;                        // ((mu - m) / sigma)^2
+        gmu[r][j] = rr;
+        glam[r][j] = e2 - 1.0f;
+        if (c1[j] + c2[j] + c3[j] > 0.f) nz |= 1u << (r * EPL + j);
+        const float gt = 1.0f - q2 - e2;                   // d loss / d sigma_log
 #pragma unroll
-      for (int k = 0; k < KC; ++k) acc[k][j] = fmaf(-xc[k], r, acc[k][j]);
-      if (!CELL) {
-        acc[T::kGB][j] -= r;
-        acc[T::kGT][j] += gt;
-      }
-      if (LOSS) acc[T::kLoss][j] += 0.5f * q2 + 0.5f * (e2 - 1.0f) - d;  // TFP _kl_normal_normal
-      if (NCELL > 0 && (g0 + j) < a.Ng) {
+        for (int k = 0; k < KC; ++k) acc[k][j] = fmaf(-xc[k], rr, acc[k][j]);
+        if (!CELL) {
+          acc[T::kGB][j] -= rr;
+          acc[T::kGT][j] += gt;
+        }
+        if (LOSS) acc[T::kLoss][j] += 0.5f * q2 + 0.5f * (e2 - 1.0f) - d;  // TFP _kl_normal_normal
+        if (NCELL > 0 && (g0 + j) < a.Ng) {
 #pragma unroll
-        for (int k = 0; k < KG; ++k) cacc[k] = fmaf(-xg[k][j], r, cacc[k]);
-        if (CELL) {
-          cacc[KG] -= r;
-          cacc[KG + 1] += gt;
+          for (int k = 0; k < KG; ++k) cacc[k] = fmaf(-xg[k][j], rr, cacc[k]);
+          if (CELL) {
+            cacc[KG] -= rr;
+            cacc[KG + 1] += gt;
+          }
         }
       }
-    }
 #endif
+      if (EXT && act != 0)   // r = (mu - m) / sigma^2 of this row, for the gradient GEMMs (frozen lanes keep their old values: unused)
+        __stcs(reinterpret_cast<Vec*>(bR + ((uint32_t)lr * ld32 + col32)), vec_make<EPL>(gmu[r]));
+      if (RPI > 1 && NCELL > 0 && lr < n_rows) cell_reduce_store(cacc, row_begin + lr);
+    }
+    if (RPI > 1 && NRC > 0) __syncwarp(); // all lanes have read the row constants before the next prefetch of these slots
 
-    if (EXT && act != 0)   // r = (mu - m) / sigma^2 of this row, for the gradient GEMMs (frozen lanes keep their old values: unused)
-      __stcs(reinterpret_cast<Vec*>(bR + ((uint32_t)lr * ld32 + col32)), vec_make<EPL>(gmu));
-
-    // ---- phase B: compacted Monte-Carlo work ----
-    uint32_t bal[EPL];
+    // ---- phase B: compacted Monte-Carlo work (the items of all RPI rows share the passes) ----
+    uint32_t bal[RPI * EPL];
     int base = 0;
 #ifdef BRIE_SKELETON   // measurement aid (scripts/ab.sh): memory skeleton only, no Monte-Carlo work
     const int n_items = 0;
 #else
     int n_items = 0;
 #pragma unroll
-    for (int j = 0; j < EPL; ++j) {
+    for (int j = 0; j < RPI * EPL; ++j) {
       bal[j] = __ballot_sync(0xffffffffu, nz & (1u << j));
       n_items += __popc(bal[j]);
     }
 #endif
     if (n_items > 0) {
 #pragma unroll
-      for (int j = 0; j < EPL; ++j) base += __popc(bal[j] & lt_mask);
-      // The queue holds tile columns only.  The row's Z_loc, Z_std_log and counts are still in this stage of
-      // the ring, so whichever lane takes an item reads them from there and leaves the Monte-Carlo sums in the
+      for (int j = 0; j < RPI * EPL; ++j) base += __popc(bal[j] & lt_mask);
+      // The queue holds (row slot, tile column) only.  The rows' Z_loc, Z_std_log and counts are still in this stage
+      // of the ring, so whichever lane takes an item reads them from there and leaves the Monte-Carlo sums in the
       // element's own count slots; an element without reads has zeros in those slots (counts are >= 0), so the
       // owners subtract their slots unconditionally afterwards.
 #pragma unroll
-      for (int j = 0; j < EPL; ++j)
-        if ((nz >> j) & 1u) q[base + __popc(nz & ((1u << j) - 1u))] = (uint32_t)(lane * EPL + j);
+      for (int j = 0; j < RPI * EPL; ++j)
+        if ((nz >> j) & 1u)
+          q[base + __popc(nz & ((1u << j) - 1u))] = (uint32_t)((j / EPL) * TC + lane * EPL + (j % EPL));
       __syncwarp();
-      float* rs = s_ring + stage * (NRA * TC);
       for (int k = lane; k < n_items; k += 32) {
-        const int col = (int)q[k];
+        const int item = (int)q[k];
+        const int r = RPI > 1 ? item / TC : 0, col = RPI > 1 ? item % TC : item;
+        float* rs = rs0 + r * SLOT;
         const float imu = rs[col], is = fast_exp(rs[TC + col]);
         const float ic1 = rs[2 * TC + col], ic2 = rs[3 * TC + col], ic3 = rs[4 * TC + col];
         const float in = ic1 + ic2 + ic3;
         const float l1 = s_L[0][col], l2 = s_L[1][col], l3 = s_L[2][col];
         float gs, ge, ls;
-        mc_samples<LOSS>(imu, is, ic1, ic2, in, l1, l2, l3, l1 - l2, a.S, s_ev[col], (uint32_t)row,
+        mc_samples<LOSS>(imu, is, ic1, ic2, in, l1, l2, l3, l1 - l2, a.S, s_ev[col], (uint32_t)(row_begin + lrb + r),
                          a.step, stream0, a.seed, gs, ge, ls);
         rs[2 * TC + col] = gs * a.inv_S;
         rs[3 * TC + col] = ge * is * a.inv_S;
@@ -818,97 +873,81 @@ __global__ void __launch_bounds__(kThreads, BRIE_MIN_CTAS) elbo_step_kernel(cons
           rs[4 * TC + col] = fmaf(ls, a.inv_S, fmaf(ic1, s_L[3][col], fmaf(ic2, s_L[4][col], ic3 * s_L[5][col])));
       }
       __syncwarp();
-      float r1[EPL], r2[EPL];
-      vec_get<EPL>(st[2 * 32], r1);
-      vec_get<EPL>(st[3 * 32], r2);
 #pragma unroll
-      for (int j = 0; j < EPL; ++j) {
-        gmu[j] -= r1[j];
-        glam[j] -= r2[j];
-      }
-      if (LOSS) {
-        float r3[EPL];
-        vec_get<EPL>(st[4 * 32], r3);
+      for (int r = 0; r < RPI; ++r) {
+        const Vec* st = reinterpret_cast<const Vec*>(rs0 + r * SLOT) + lane;
+        float r1[EPL], r2[EPL];
+        vec_get<EPL>(st[2 * 32], r1);
+        vec_get<EPL>(st[3 * 32], r2);
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) acc[T::kLoss][j] -= r3[j];
+        for (int j = 0; j < EPL; ++j) {
+          gmu[r][j] -= r1[j];
+          glam[r][j] -= r2[j];
+        }
+        if (LOSS) {
+          float r3[EPL];
+          vec_get<EPL>(st[4 * 32], r3);
+#pragma unroll
+          for (int j = 0; j < EPL; ++j) acc[T::kLoss][j] -= r3[j];
+        }
       }
     }
 
     // ---- phase C: Adam on Z_loc / Z_std_log, clip, store ----
-    if (act != 0) {
-      float m1[EPL], v1[EPL], m2[EPL], v2[EPL];
-      vec_get<EPL>(st[5 * 32], m1);
-      vec_get<EPL>(st[6 * 32], v1);
-      vec_get<EPL>(st[7 * 32], m2);
-      vec_get<EPL>(st[8 * 32], v2);
-      if (all_act) {
+#pragma unroll
+    for (int r = 0; r < RPI; ++r) {
+      const int lr = lrb + r;
+      if (act != 0 && (RPI == 1 || lr < n_rows)) {
+        const Vec* st = reinterpret_cast<const Vec*>(rs0 + r * SLOT) + lane;
+        float m1[EPL], v1[EPL], m2[EPL], v2[EPL];
+        vec_get<EPL>(st[5 * 32], m1);
+        vec_get<EPL>(st[6 * 32], v1);
+        vec_get<EPL>(st[7 * 32], m2);
+        vec_get<EPL>(st[8 * 32], v2);
+        if (all_act) {
 #if BRIE_F32X2
 #pragma unroll
-        for (int p = 0; p < EPL / 2; ++p) {
-          const int j0 = 2 * p, j1 = 2 * p + 1;
-          adam_update2(mu[j0], mu[j1], m1[j0], m1[j1], v1[j0], v1[j1], gmu[j0], gmu[j1], a.alpha);
-          adam_update2(lam[j0], lam[j1], m2[j0], m2[j1], v2[j0], v2[j1], glam[j0], glam[j1], a.alpha);
-          mu[j0] = clip9(mu[j0]);  // Variable constraint (model_TFProb.py:80-81)
-          mu[j1] = clip9(mu[j1]);
-        }
+          for (int p = 0; p < EPL / 2; ++p) {
+            const int j0 = 2 * p, j1 = 2 * p + 1;
+            adam_update2(mu[r][j0], mu[r][j1], m1[j0], m1[j1], v1[j0], v1[j1], gmu[r][j0], gmu[r][j1], a.alpha);
+            adam_update2(lam[r][j0], lam[r][j1], m2[j0], m2[j1], v2[j0], v2[j1], glam[r][j0], glam[r][j1], a.alpha);
+            mu[r][j0] = clip9(mu[r][j0]);  // Variable constraint (model_TFProb.py:80-81)
+            mu[r][j1] = clip9(mu[r][j1]);
+          }
 #else
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) {
-          adam_update(mu[j], m1[j], v1[j], gmu[j], a.alpha);
-          adam_update(lam[j], m2[j], v2[j], glam[j], a.alpha);
-          mu[j] = clip9(mu[j]);  // Variable constraint (model_TFProb.py:80-81)
-        }
+          for (int j = 0; j < EPL; ++j) {
+            adam_update(mu[r][j], m1[j], v1[j], gmu[r][j], a.alpha);
+            adam_update(lam[r][j], m2[j], v2[j], glam[r][j], a.alpha);
+            mu[r][j] = clip9(mu[r][j]);  // Variable constraint (model_TFProb.py:80-81)
+          }
 #endif
-      } else {
+        } else {
 #pragma unroll
-        for (int j = 0; j < EPL; ++j) {
-          if ((act >> j) & 1u) {
-            adam_update(mu[j], m1[j], v1[j], gmu[j], a.alpha);
-            adam_update(lam[j], m2[j], v2[j], glam[j], a.alpha);
-            mu[j] = clip9(mu[j]);
+          for (int j = 0; j < EPL; ++j) {
+            if ((act >> j) & 1u) {
+              adam_update(mu[r][j], m1[j], v1[j], gmu[r][j], a.alpha);
+              adam_update(lam[r][j], m2[j], v2[j], glam[r][j], a.alpha);
+              mu[r][j] = clip9(mu[r][j]);
+            }
           }
         }
-      }
-      const uint32_t rel = (uint32_t)lr * ld32 + col32;
-      __stcs(reinterpret_cast<Vec*>(bZl + rel), vec_make<EPL>(mu));
-      __stcs(reinterpret_cast<Vec*>(bZs + rel), vec_make<EPL>(lam));
-      __stcs(reinterpret_cast<Vec*>(bA0 + rel), vec_make<EPL>(m1));
-      __stcs(reinterpret_cast<Vec*>(bA1 + rel), vec_make<EPL>(v1));
-      __stcs(reinterpret_cast<Vec*>(bA2 + rel), vec_make<EPL>(m2));
-      __stcs(reinterpret_cast<Vec*>(bA3 + rel), vec_make<EPL>(v2));
-    }
-    if (NCELL > 0) {
-      float* pc = a.part_cell + (((int64_t)tile * a.M + m) * a.Nc + row) * NCELL;
-      if (KG > 0) {
-        // Halving butterfly: slot i of this lane holds feature i ^ pk, so at every step all lanes keep
-        // the lower half of their slots and hand the upper half to the partner that keeps those features
-        // (no selects); KG - 1 + log2(32 / KG) shuffles instead of 5 KG.
-#pragma unroll
-        for (int t = 0; t < KGB; ++t) {
-          const int H = KG >> (t + 1);
-#pragma unroll
-          for (int i = 0; i < H; ++i) cacc[i] += __shfl_xor_sync(0xffffffffu, cacc[H + i], 16 >> t);
-        }
-        float s = cacc[0];
-#pragma unroll
-        for (int o = 16 >> KGB; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if ((lane & ((32 >> KGB) - 1)) == 0) pc[pk] = s;
-      }
-      if (CELL) {  // d/d intercept and d/d sigma_log of the cell: two values, one per half-warp after the first step
-        const bool hi = (lane & 16) != 0;
-        const float keep = hi ? cacc[KG + 1] : cacc[KG], send = hi ? cacc[KG] : cacc[KG + 1];
-        float s = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-#pragma unroll
-        for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if ((lane & 15) == 0) pc[KG + (hi ? 1 : 0)] = s;
+        const uint32_t rel = (uint32_t)lr * ld32 + col32;
+        __stcs(reinterpret_cast<Vec*>(bZl + rel), vec_make<EPL>(mu[r]));
+        __stcs(reinterpret_cast<Vec*>(bZs + rel), vec_make<EPL>(lam[r]));
+        __stcs(reinterpret_cast<Vec*>(bA0 + rel), vec_make<EPL>(m1));
+        __stcs(reinterpret_cast<Vec*>(bA1 + rel), vec_make<EPL>(v1));
+        __stcs(reinterpret_cast<Vec*>(bA2 + rel), vec_make<EPL>(m2));
+        __stcs(reinterpret_cast<Vec*>(bA3 + rel), vec_make<EPL>(v2));
       }
     }
+    if (RPI == 1 && NCELL > 0) cell_reduce_store(cacc1, row_begin + lrb);
   }
   cp_async_wait<0>();
 
   if (NEV > 0) {
     __syncthreads();  // all warps are done with their queues; reuse the memory for the reduction
-    float(*red)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * NRA * TC);
+    float(*red)[TC] = reinterpret_cast<float(*)[TC]>(smem + kWarps * kRingStages * RPI * SLOT);
     const int64_t gcol = thread_col();
 #pragma unroll
     for (int i = 0; i < NEV; ++i) {

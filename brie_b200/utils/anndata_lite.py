@@ -84,22 +84,51 @@ class AnnDataLite:
                     list(self.obsm), list(self.varm), list(self.layers)))
 
     # ---- persistence (npz; `anndata`/`h5py` are not installable in this image) ----
-    def write_npz(self, path):
+    @staticmethod
+    def _put(d, key, v):
+        """One array-like into the npz dict: sparse matrices stay sparse (CSC / CSR components), memory-mapped
+        (cells, events) output layers (fitBRIE out_dir) are referenced by path -- densifying or embedding either
+        costs 80 GB per matrix at atlas scale -- everything else as a dense array."""
         from scipy.sparse import issparse
-        d = {"X": self.X.toarray() if issparse(self.X) else np.asarray(self.X),
-             "obs_index": np.asarray(self.obs.index, dtype=str), "var_index": np.asarray(self.var.index, dtype=str)}
+        if issparse(v):
+            v = v.tocsc() if v.format not in ('csc', 'csr') else v
+            d[key + "@sparse/data"], d[key + "@sparse/indices"], d[key + "@sparse/indptr"] = v.data, v.indices, v.indptr
+            d[key + "@sparse/meta"] = np.array([v.shape[0], v.shape[1], 0 if v.format == 'csc' else 1], np.int64)
+        elif isinstance(v, np.memmap) and v.filename is not None:
+            d[key + "@memmap"] = np.asarray(str(v.filename))
+        else:
+            d[key] = np.asarray(v)
+
+    @staticmethod
+    def _get_all(z, prefix):
+        """{name: array} of everything stored under `prefix/` by _put."""
+        from scipy.sparse import csc_matrix, csr_matrix
+        out = {}
+        for k in z.files:
+            if not k.startswith(prefix + "/"):
+                continue
+            name = k[len(prefix) + 1:]
+            if name.endswith("@memmap"):
+                out[name[:-7]] = np.load(str(z[k]), mmap_mode='r')
+            elif name.endswith("@sparse/meta"):
+                base = k[:-len("/meta")]
+                r, c, fmt = (int(x) for x in z[k])
+                cls = csc_matrix if fmt == 0 else csr_matrix
+                out[name[:-len("@sparse/meta")]] = cls((z[base + "/data"], z[base + "/indices"], z[base + "/indptr"]), shape=(r, c))
+            elif "@sparse/" not in name:
+                out[name] = z[k]
+        return out
+
+    def write_npz(self, path):
+        d = {"obs_index": np.asarray(self.obs.index, dtype=str), "var_index": np.asarray(self.var.index, dtype=str)}
+        self._put(d, "main/X", self.X)
         for c in self.obs.columns:
             d["obs/" + c] = np.asarray(self.obs[c])
         for c in self.var.columns:
             d["var/" + c] = np.asarray(self.var[c])
         for grp, dic in (("obsm", self.obsm), ("varm", self.varm), ("layers", self.layers)):
             for k, v in dic.items():
-                if isinstance(v, np.memmap) and v.filename is not None:
-                    # a memory-mapped (cells, events) output layer (fitBRIE out_dir): keep it where it is
-                    # and store its path -- embedding it would densify 80 GB per layer at atlas scale
-                    d[grp + "_memmap/" + k] = np.asarray(str(v.filename))
-                    continue
-                d[grp + "/" + k] = v.toarray() if issparse(v) else np.asarray(v)
+                self._put(d, grp + "/" + k, v)
         d["uns"] = np.array(self.uns, dtype=object)
         np.savez_compressed(path, **d)
 
@@ -110,10 +139,6 @@ class AnnDataLite:
         z = np.load(path, allow_pickle=True)
         obs = pd.DataFrame({k[4:]: z[k] for k in z.files if k.startswith("obs/")}, index=z["obs_index"])
         var = pd.DataFrame({k[4:]: z[k] for k in z.files if k.startswith("var/")}, index=z["var_index"])
-        def pick(g):
-            out = {k[len(g) + 1:]: z[k] for k in z.files if k.startswith(g + "/")}
-            for k in z.files:
-                if k.startswith(g + "_memmap/"):
-                    out[k[len(g) + 8:]] = np.load(str(z[k]), mmap_mode='r')
-            return out
-        return cls(z["X"], obs, var, pick("obsm"), pick("varm"), pick("layers"), z["uns"].item())
+        X = cls._get_all(z, "main")["X"] if any(k.startswith("main/") for k in z.files) else z["X"]
+        return cls(X, obs, var, cls._get_all(z, "obsm"), cls._get_all(z, "varm"), cls._get_all(z, "layers"),
+                   z["uns"].item())

@@ -21,6 +21,14 @@ SHAPES = {
     "C3": dict(Nc=100000, Ng=2048, design='mixed3', eff=True, layers=3,
                masks=[[0, 1, 2], [1, 2], [0, 2], [0, 1]], mode='gene', Kg=0),
     "C4": dict(Nc=200000, Ng=4096, design='none', eff=False, layers=2, masks=[[]], mode='cell', Kg=8),
+    "C3F": dict(Nc=100000, Ng=10000, design='mixed3', eff=True, layers=3,
+                masks=[[0, 1, 2], [1, 2], [0, 2], [0, 1]], mode='gene', Kg=0),      # the whole C3 on one GPU (108 GB)
+    "C3a": dict(Nc=100000, Ng=2500, design='mixed3', eff=True, layers=3,
+                masks=[[0, 1, 2], [1, 2], [0, 2], [0, 1]], mode='gene', Kg=0),      # ld 2528: rows 128-byte aligned only
+    "C3b": dict(Nc=100000, Ng=2560, design='mixed3', eff=True, layers=3,
+                masks=[[0, 1, 2], [1, 2], [0, 2], [0, 1]], mode='gene', Kg=0),      # ld 2560: 20 whole tiles
+    "C3H": dict(Nc=100000, Ng=5000, design='mixed3', eff=True, layers=3,
+                masks=[[0, 1, 2], [1, 2], [0, 2], [0, 1]], mode='gene', Kg=0),
     "W16": dict(Nc=20000, Ng=4096, design='wide15', eff=False, layers=2, masks=[list(range(15))], mode='gene', Kg=0),
     "C5": dict(Nc=1000000, Ng=512, design='pseudotime', eff=True, layers=3, masks=[[0], []], mode='gene', Kg=0),
     # wide designs (contractions as GEMMs around the fused kernel): 24 cell covariates; 20 gene features + cell intercept

@@ -362,11 +362,19 @@ def test_npz_container_references_memmapped_layers(tmp_path):
     ad.write_npz(out)
     assert os.path.getsize(out) < 4096                                   # the map is referenced, not embedded
     z = np.load(out, allow_pickle=True)
-    assert 'layers_memmap/Psi' in z.files and 'layers/Psi' not in z.files
+    assert 'layers/Psi@memmap' in z.files and 'layers/Psi' not in z.files
     back = AnnDataLite.read_npz(out)
     assert isinstance(back.layers['Psi'], np.memmap)
     assert np.array_equal(np.asarray(back.layers['Psi']), np.asarray(mm))
     assert np.array_equal(back.layers['isoform1'], X)
+    # sparse matrices stay sparse in the container (a 1M x 20k count matrix is 80 GB dense)
+    from scipy.sparse import csc_matrix, issparse
+    ads = AnnDataLite(X=csc_matrix(X), layers={'isoform1': csc_matrix(X), 'dense': X.copy()})
+    outs = str(tmp_path / "sparse.npz")
+    ads.write_npz(outs)
+    backs = AnnDataLite.read_npz(outs)
+    assert issparse(backs.X) and issparse(backs.layers['isoform1']) and not issparse(backs.layers['dense'])
+    assert np.array_equal(backs.X.toarray(), X) and np.array_equal(backs.layers['isoform1'].toarray(), X)
 
 
 def test_host_pseudo_count_side_effect_semantics():
