@@ -97,6 +97,17 @@ SYMBOLS = {
     "brie_scatter_events": (C.c_int, [C.c_int64, C.c_int64, _P, _P, C.c_int64, C.c_int64, _P, _P]),
 }
 
+def leading_dim(n_events):
+    """Leading dimension (floats) of the (cells, events) device arrays: rows start 512-byte aligned.
+
+    A warp's row segment is 128 floats = 512 B per array.  With rows only 128-byte aligned (ld a multiple of 32) the
+    same kernel ran 5 % slower on one B200 (C3 slab, 100 000 x 2 500, ld 2 528: 0.909 of the HBM peak; 100 000 x 2 560,
+    ld 2 560: 0.958; profiles/r2_ab_rpi_tma.md) -- the full-size C3 (ld 10 016) paid the same.  Padding columns are
+    inactive: their lanes copy nothing, so the padding costs memory (at most 127 columns), not traffic."""
+    n = int(n_events)
+    return (n + 127) // 128 * 128 if n > 96 else (n + 31) // 32 * 32
+
+
 _lib = None
 
 

@@ -97,7 +97,7 @@ class FitEngine:
         if n_events is not None:          # device tensors already padded to (Nc, ld), e.g. from the simulator
             Ng = int(n_events)
         self.Nc, self.Ng = int(Nc), int(Ng)
-        self.ld = _round_up(self.Ng, 32)
+        self.ld = _lib.leading_dim(self.Ng)
         self.event_offset = int(event_offset)
         self.n_events_total = int(n_events_total) if n_events_total is not None else self.event_offset + self.Ng
         self.n_layers = len(counts)
@@ -382,9 +382,9 @@ class FitEngine:
         if not force and not gathered_round_is_cheaper(cols, self.Ng, Nc, L, n_steps):
             return False
         per_col = M * Nc * (L + 6) * 4 * 1.05 + M * (n_steps + 64) * 4
-        max_ld = int(0.8 * self._free_bytes() / per_col) // 32 * 32
+        max_ld = int(0.8 * self._free_bytes() / per_col) // 128 * 128
         nmax = max(len(c) for c in cols)
-        if max_ld < min(_round_up(nmax, 32), 256):
+        if max_ld < min(_lib.leading_dim(nmax), 256):
             return False
         n_parts = -(-nmax // max_ld)
         todo = [[np.array_split(c, n_parts)[k] for c in cols] for k in range(n_parts)]
@@ -560,7 +560,7 @@ class _GatheredFit:
         M, Nc, L, Kc = p.M, p.Nc, p.n_layers, p.Kc
         self.n = [len(c) for c in cols]
         nmax = max(max(self.n), 1)
-        ld = self.ld = _round_up(nmax, 32)
+        ld = self.ld = _lib.leading_dim(nmax)
         self.n_moves = 0
 
         d = _lib.FitDesc()

@@ -45,7 +45,7 @@ def layer_to_device(layer, e0, e1, device, ld=None):
     device = torch.device(device)
     Nc = int(layer.shape[0])
     n = int(e1 - e0)
-    ld = _round_up(n, 32) if ld is None else int(ld)
+    ld = _lib.leading_dim(n) if ld is None else int(ld)
     with torch.cuda.device(device):
         if issparse(layer):
             if not (isspmatrix_csc(layer) or isspmatrix_csr(layer)):
@@ -111,7 +111,7 @@ def gather_events(tile, keep_idx):
     dev = tile.device
     keep_idx = np.asarray(keep_idx, np.int64)
     n_out = int(keep_idx.size)
-    ld_out = max(_round_up(n_out, 32), 32)
+    ld_out = max(_lib.leading_dim(n_out), 32)
     with torch.cuda.device(dev):
         src = torch.from_numpy(keep_idx).to(dev)
         out = torch.empty((tile.shape[0], ld_out), dtype=torch.float32, device=dev)

@@ -61,7 +61,7 @@ def simulator(adata, Psi=None, effLen=None, mode="posterior",
     lib = _lib.load()
     dev = torch.device(device if device is not None else "cuda")
     Nc, Ng = adata.shape
-    ld = (Ng + 31) // 32 * 32
+    ld = _lib.leading_dim(Ng)
     out = adata.copy()
     total = np.zeros((Nc, ld), np.float32)
     for key in layer_keys:

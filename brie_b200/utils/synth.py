@@ -90,7 +90,7 @@ def simulate_counts_device(Nc, Ng, design='none', seed=0, with_efflen=True, n_la
     else:                                  # a design shared by several event blocks (seed = block)
         Xc = np.asarray(Xc, np.float32)
     Kc = Xc.shape[1]
-    ld = (Ng + 31) // 32 * 32
+    ld = _lib.leading_dim(Ng)
     pad = lambda v, fill=0.0: np.concatenate([v, np.full(ld - Ng, fill)]).astype(np.float32)
     b = rng.normal(0, 3.0, Ng)
     Wc = rng.standard_normal((Kc, Ng)) * (rng.uniform(size=(1, Ng)) < effect_frac)

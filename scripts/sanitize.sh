@@ -16,6 +16,11 @@ from util import make_problem, make_lrt_problem
 data, effLen, Xc, Xg = make_problem(70, 45, 9, 5, False, 2, seed=3)
 fit_BRIE_matrix([x.copy() for x in data], Xc=Xc, Xg=Xg, intercept_mode='cell', LRT_index=[], min_iter=12, max_iter=12,
                 MC_size=3, n_eval=3)
+# the two-rows-per-iteration form (Kc 11 -> 16 without gene features; Kc 8 with gene features) and a wide design (GEMM form)
+for kc, kg, mode in ((11, 0, 'gene'), (8, 3, 'gene'), (20, 0, 'gene')):
+    data, effLen, Xc, Xg = make_problem(70, 45, kc, kg, True, 3, seed=4)
+    fit_BRIE_matrix([x.copy() for x in data], Xc=Xc, Xg=Xg if kg else None, effLen=effLen, intercept_mode=mode, LRT_index=[],
+                    min_iter=12, max_iter=12, MC_size=3, n_eval=3)
 # batched LRT with convergence groups: extension rounds in place (active-block list) and on gathered sub-fits
 from brie_b200.engine import FitEngine
 from oracle.brie2_oracle import add_pseudo_count

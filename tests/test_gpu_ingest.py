@@ -7,6 +7,7 @@ import os
 import numpy as np
 import pytest
 
+from brie_b200 import _lib
 from oracle.brie2_oracle import add_pseudo_count
 
 pytestmark = pytest.mark.gpu
@@ -37,7 +38,7 @@ def test_sparse_scatter_equals_toarray(fmt, idx_dtype, val_dtype):
     for e0, e1 in [(0, Ng), (0, 1), (33, 129), (Ng - 5, Ng)]:
         t, nbytes = layer_to_device(m, e0, e1, "cuda")
         got = t.cpu().numpy()
-        assert got.shape == (Nc, (e1 - e0 + 31) // 32 * 32)
+        assert got.shape == (Nc, _lib.leading_dim(e1 - e0))
         assert np.array_equal(got[:, :e1 - e0], dense[:, e0:e1])
         assert not got[:, e1 - e0:].any(), "padding must hold zero counts"
         assert nbytes > 0
