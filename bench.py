@@ -446,7 +446,13 @@ def e2e_leg(ctx, name, min_iter, out_root):
            "api": "brie_b200.models.fitBRIE(AnnData with host scipy CSC layers) -> device ingest, full schedule, "
                   "per-batch convergence extensions, loss_gene, LRT, p/FDR, D2H of 4 dense layers into .npy maps",
            "fdr05_calls": [int(v) for v in (np.asarray(res.fdr) < 0.05).sum(0)], "outputs_finite": psi_ok,
-           "output_maps": out_dir}
+           "output_maps": out_dir + " (removed after the run)"}
+    del res
+    ad.layers.clear()
+    ctx.barrier()
+    if ctx.rank == 0:                              # 4 x (cells, events) float32 maps: do not leave them on the box
+        import shutil
+        shutil.rmtree(out_dir, ignore_errors=True)
     return out
 
 
@@ -528,13 +534,14 @@ def main():
                "value_at_nproc_6": v6, "note": "restated reference, PyTorch-CPU eager -- not TensorFlow"}
 
     if ctx.rank == 0:
-        cfg = config_dict(ctx.world)
-        cfg.update({"events_this_rank": hi - lo, "nonzero_fraction": nz, "resident_GB_per_gpu": state_gb})
+        cfg = config_dict(ctx.world)                 # identical to the reference arm's
+        run_info = {"events_this_rank": hi - lo, "nonzero_fraction": nz, "resident_GB_per_gpu": state_gb}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": ctx.world, "steps": K, "warmup": W,
                "ms_per_step": r["ms"] / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "f32", "data": "synthetic", "config": cfg,
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-               "cpu_baseline": cpu, "fit_lrt_wall_s": e2e["wall_s"] if e2e else None, "shapes": shapes, "c4": c4}
+               "cpu_baseline": cpu, "fit_lrt_wall_s": e2e["wall_s"] if e2e else None, "shapes": shapes, "c4": c4,
+               "run_info": run_info}
         print(json.dumps(out))
     if ctx.dist is not None:
         ctx.dist.barrier()

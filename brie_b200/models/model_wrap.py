@@ -167,6 +167,27 @@ def _host_pseudo_count_inplace(data, pseudo_count):
         np.add(data[i], pseudo_count, out=data[i], where=idx, casting='unsafe')
 
 
+def _engine_plan(base_cols, test_masks, cell_mode, intercept_mode, max_models=None):
+    """[(column masks, model ids, intercept mode)] per FitEngine: the base model (id 0) with as many LRT refits
+    (ids 1..T) as one launch batches, the remaining refits in further engines of at most `max_models` models; a
+    cell-mode base model sits alone, because the reference's refits always use the per-event layout
+    (model_wrap.py:174-178)."""
+    if max_models is None:
+        from .._lib import BRIE_MAX_MODELS as max_models
+    T = len(test_masks)
+    plan = []
+    if cell_mode and T > 0:
+        plan.append(([base_cols], [0], intercept_mode))
+        first_tests = 0
+    else:
+        first_tests = min(T, max_models - 1)
+        plan.append(([base_cols] + test_masks[:first_tests], list(range(first_tests + 1)), intercept_mode))
+    for t0 in range(first_tests, T, max_models):
+        t1 = min(t0 + max_models, T)
+        plan.append((test_masks[t0:t1], list(range(1 + t0, 1 + t1)), 'gene'))
+    return plan
+
+
 def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
                     intercept_mode='gene', LRT_index=None, pseudo_count=0.01,
                     sigma=None, base_mode='full', tau_prior=[3, 27], **keyargs):
@@ -273,17 +294,7 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     # that runs the remaining refits in further engines, one after the other, over the same device tiles.
     # NB the reference builds the refits WITHOUT intercept_mode (model_wrap.py:174-178), so they always use
     # the default per-event ('gene') intercept/sigma layout: a cell-mode base model gets an engine of its own.
-    from .._lib import BRIE_MAX_MODELS
-    plan = []
-    if cell_mode and T > 0:
-        plan.append(([base_cols], [0], intercept_mode))
-        first_tests = 0
-    else:
-        first_tests = min(T, BRIE_MAX_MODELS - 1)
-        plan.append(([base_cols] + test_masks[:first_tests], list(range(first_tests + 1)), intercept_mode))
-    for t0 in range(first_tests, T, BRIE_MAX_MODELS):
-        t1 = min(t0 + BRIE_MAX_MODELS, T)
-        plan.append((test_masks[t0:t1], list(range(1 + t0, 1 + t1)), 'gene'))
+    plan = _engine_plan(base_cols, test_masks, cell_mode, intercept_mode)
     t_ph = _tick("engine_setup", t_ph)
 
     brie_results = None

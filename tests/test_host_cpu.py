@@ -400,3 +400,24 @@ def test_cli_has_outdir_and_resume_flags():
     assert out.returncode == 0
     for flag in ("--outDir", "--resume", "--LRTindex", "--testBase", "--interceptMode", "--MCsize", "--batchSize"):
         assert flag in out.stdout, flag
+
+
+def test_engine_plan_splits_long_lrt_lists():
+    """fit_BRIE_matrix batches the base model and the LRT refits into FitEngines of at most 32 models; a one-vs-rest
+    LRT over more covariates runs the remaining refits in further engines (the reference loops over any number of
+    tests, model_wrap.py:156-187); a cell-mode base model sits alone (refits use the per-event layout, :174-178)."""
+    from brie_b200.models.model_wrap import _engine_plan
+    tests = [[k for k in range(40) if k != i] for i in range(40)]
+    plan = _engine_plan(list(range(40)), tests, False, 'gene')
+    assert [len(p[0]) for p in plan] == [32, 9]
+    assert plan[0][1] == list(range(32)) and plan[1][1] == list(range(32, 41))
+    assert plan[0][0][0] == list(range(40)) and plan[0][0][1] == tests[0] and plan[1][0][0] == tests[31]
+    assert sorted(i for p in plan for i in p[1]) == list(range(41))              # every model exactly once
+    plan = _engine_plan([0], [[0, 1], [0, 2]], True, 'cell')
+    assert [(p[1], p[2]) for p in plan] == [([0], 'cell'), ([1, 2], 'gene')]
+    plan = _engine_plan([0, 1], [], True, 'cell')
+    assert plan == [([[0, 1]], [0], 'cell')]
+    plan = _engine_plan([], [[0]], False, 'None', max_models=2)
+    assert [(p[0], p[1]) for p in plan] == [([[], [0]], [0, 1])]
+    plan = _engine_plan([], [[0], [1], [2]], False, 'gene', max_models=2)
+    assert [p[1] for p in plan] == [[0, 1], [2, 3]]
