@@ -105,7 +105,8 @@ def leading_dim(n_events):
     ld 2 560: 0.958; profiles/r2_ab_rpi_tma.md) -- the full-size C3 (ld 10 016) paid the same.  Padding columns are
     inactive: their lanes copy nothing, so the padding costs memory (at most 127 columns), not traffic."""
     n = int(n_events)
-    return (n + 127) // 128 * 128 if n > 96 else (n + 31) // 32 * 32
+    align = int(os.environ.get("BRIE_LD_ALIGN", "128"))        # measurement aid (multiple of 32)
+    return (n + align - 1) // align * align if n > 96 else (n + 31) // 32 * 32
 
 
 _lib = None

@@ -124,10 +124,26 @@ def concate(BRIE_RV_list):
     return res_merge
 
 
+class _ChunkSink:
+    """Where fit_BRIE_matrix leaves the dense layers of one event chunk when fitBRIE drives it: the chunk's column
+    range of a LayerStore, copied by a background thread so that the transfer overlaps the next chunk's fit.
+    `before_outputs` is called before this chunk's output tensors are allocated (fitBRIE waits for the previous
+    chunk's copy there, so at most one chunk's outputs are alive on the device at a time)."""
+
+    def __init__(self, store, e0, before_outputs=None, background=True):
+        self.store, self.e0, self.before_outputs, self.background = store, e0, before_outputs, background
+        self.copy = None
+
+    def wait(self):
+        if self.copy is not None:
+            self.copy.wait()
+            self.copy = None
+
+
 def _rv_from_engine(eng, m, Xc_model, Xg, intercept_mode, sink=None):
     """Result container of model m.  The dense (cells, events) arrays Psi / Psi95CI / Z_std / Z_loc go to the host
-    through pinned staging (utils/d2h.py): into fresh arrays, or -- `sink` = (LayerStore, first event) -- straight
-    into their column range of the store's arrays / memory maps, leaving (cells, 0) stubs in the container."""
+    through pinned staging (utils/d2h.py): into fresh arrays, or -- `sink` a _ChunkSink -- straight into their
+    column range of the store's arrays / memory maps, leaving (cells, 0) stubs in the container."""
     from ..utils import d2h
     rv = BRIE_RV()
     rv.Nc, rv.Ng = eng.Nc, eng.Ng
@@ -137,19 +153,29 @@ def _rv_from_engine(eng, m, Xc_model, Xg, intercept_mode, sink=None):
     p = eng.model_params(m)
     rv.sigma, rv.intercept = p['sigma'], p['intercept']
     rv.cell_coeff, rv.gene_coeff = p['Wc_loc'], p['Wg_loc']
-    Psi, CI, Zstd = eng.posterior(m)
-    big = dict(Psi=Psi, Psi95CI=CI, Z_std=Zstd, Z_loc=eng.Z_loc[m, :, :eng.Ng])
-    for k, t in big.items():
-        if sink is None:
-            setattr(rv, k, d2h.to_host(t))
-        else:
-            store, e0 = sink
-            if k in store.arrays:
-                d2h.to_host_columns(t, store.arrays[k], e0)
-            setattr(rv, k, np.zeros((rv.Nc, 0), np.float32))
     rv.losses = eng.losses[m]
     rv.loss_gene = eng.loss_gene[m].cpu().numpy()
     rv.intercept_mode = intercept_mode
+    if sink is not None and sink.before_outputs is not None:
+        sink.before_outputs()
+    Psi, CI, Zstd = eng.posterior(m)
+    big = dict(Psi=Psi, Psi95CI=CI, Z_std=Zstd, Z_loc=eng.Z_loc[m, :, :eng.Ng])
+    if sink is None:
+        for k, t in big.items():
+            setattr(rv, k, d2h.to_host(t))
+        return rv
+    jobs = []
+    for k, t in big.items():
+        if k in sink.store.arrays:
+            if k == 'Z_loc' and sink.background:
+                t = t.clone()                      # the engine's state is freed while the copy is still running
+            jobs.append((t, sink.store.arrays[k], sink.e0))
+        setattr(rv, k, np.zeros((rv.Nc, 0), np.float32))
+    if sink.background:
+        sink.copy = d2h.BackgroundCopy(jobs, eng.device)
+    else:
+        for t, dst, c0 in jobs:
+            d2h.to_host_columns(t, dst, c0)
     return rv
 
 
@@ -212,7 +238,7 @@ def fit_BRIE_matrix(data, Xc=None, Xg=None, effLen=None, intercept=None,
     MC_size = keyargs.pop('MC_size', 1)
     target = keyargs.pop('target', "ELBO")                          # reaches BRIE2.fit through **keyargs (:144)
     host_side_effect = keyargs.pop('host_side_effect', True)
-    out_sink = keyargs.pop('out_sink', None)                        # (LayerStore, first event): fitBRIE's output arrays
+    out_sink = keyargs.pop('out_sink', None)                        # _ChunkSink: fitBRIE's output arrays
     for k in ('optimizer', 'learn_rate', 'verbose'):                # accepted and ignored (:214-237)
         keyargs.pop(k, None)
 
@@ -452,6 +478,19 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
                                    pseudo_count, sigma, base_mode, keyargs) if out_dir is not None else None
         store = LayerStore(Nc, Ng, out_dir, rank, world, dist, keys=out_keys, signature=signature, resume=resume)
         res_list = []
+        pending = None                     # (sink, result) of the chunk whose layers are still on their way to the host
+
+        def _land():
+            nonlocal pending
+            if pending is not None:
+                _sink, _res = pending
+                pending = None
+                _t0 = time.perf_counter()
+                _sink.wait()
+                store.put(_sink.e0, _res)  # (checkpoint marker only after the chunk's layers are in the maps)
+                if getattr(_res, 'timing', None) is not None:
+                    _res.timing['store.put'] = time.perf_counter() - _t0
+
         for e0 in range(lo, hi, chunk):
             _done = store.load_chunk(e0, min(e0 + chunk, hi))
             if _done is not None:
@@ -461,18 +500,22 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
             _idx = slice(e0, min(e0 + chunk, hi))
             _count_layers = [adata.layers[_key][:, _idx] for _key in layer_keys]
             _effLen = adata.varm['effLen'][_idx, :] if 'effLen' in adata.varm else None
-            _ResVal = fit_BRIE_matrix(
-                _count_layers, Xc=Xc, Xg=Xg[_idx, :], effLen=_effLen,
-                intercept=intercept, intercept_mode=intercept_mode,
-                LRT_index=LRT_index, pseudo_count=pseudo_count, sigma=sigma,
-                base_mode=base_mode, tau_prior=tau_prior, group_size=_n_gene,
-                event_offset=e0, n_events_total=Ng, host_side_effect=False, out_sink=(store, e0), **keyargs)
-            _t0 = time.perf_counter()
-            store.put(e0, _ResVal)
-            if getattr(_ResVal, 'timing', None) is not None:
-                _ResVal.timing['store.put'] = time.perf_counter() - _t0
+            # the previous chunk's layers land (and its checkpoint is written) while this chunk is fitted: at the
+            # latest before this chunk's own output tensors are allocated, and also if this fit dies
+            _sink = _ChunkSink(store, e0, before_outputs=_land)
+            try:
+                _ResVal = fit_BRIE_matrix(
+                    _count_layers, Xc=Xc, Xg=Xg[_idx, :], effLen=_effLen,
+                    intercept=intercept, intercept_mode=intercept_mode,
+                    LRT_index=LRT_index, pseudo_count=pseudo_count, sigma=sigma,
+                    base_mode=base_mode, tau_prior=tau_prior, group_size=_n_gene,
+                    event_offset=e0, n_events_total=Ng, host_side_effect=False, out_sink=_sink, **keyargs)
+            finally:
+                _land()
+            pending = (_sink, _ResVal)
             res_list.append(_ResVal)
             print("[BRIE2] %d out %d genes done" % (min(e0 + chunk, hi) - lo, hi - lo))
+        _land()
         if world > 1:                      # per-event vectors: every rank gets all of them, in event order
             parts = [None] * world
             dist.all_gather_object(parts, res_list)
@@ -494,7 +537,7 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
             intercept_mode=intercept_mode, LRT_index=LRT_index,
             pseudo_count=pseudo_count, sigma=sigma, base_mode=base_mode,
             tau_prior=tau_prior, event_offset=lo, n_events_total=Ng,
-            dist_group=dist.group.WORLD, out_sink=(store, lo), **keyargs)
+            dist_group=dist.group.WORLD, out_sink=_ChunkSink(store, lo, background=False), **keyargs)
         store.put(lo, local, checkpoint=False)
         parts = [None] * world
         dist.all_gather_object(parts, local)

@@ -22,8 +22,9 @@ def _buffers(device, n_floats):
     return cur
 
 
-def to_host_columns(src, dst, col0=0):
-    """dst[:, col0:col0 + n] = src, src a (rows, n) float32 device tensor (any row stride), dst a host array."""
+def to_host_columns(src, dst, col0=0, after=None):
+    """dst[:, col0:col0 + n] = src, src a (rows, n) float32 device tensor (any row stride), dst a host array.
+    `after`: CUDA event the producer of `src` recorded (default: everything enqueued on the current stream so far)."""
     rows, n = src.shape
     if rows == 0 or n == 0:
         return
@@ -31,7 +32,10 @@ def to_host_columns(src, dst, col0=0):
     per = max(1, min(rows, SLAB_BYTES // (n * 4)))
     bufs = _buffers(dev, per * n)
     side = torch.cuda.Stream(dev)
-    side.wait_stream(torch.cuda.current_stream(dev))
+    if after is not None:
+        side.wait_event(after)
+    else:
+        side.wait_stream(torch.cuda.current_stream(dev))
     evs = [torch.cuda.Event(), torch.cuda.Event()]
     slabs = [(r0, min(r0 + per, rows)) for r0 in range(0, rows, per)]
 
@@ -55,3 +59,29 @@ def to_host(src):
     out = np.empty(tuple(src.shape), np.float32)
     to_host_columns(src, out, 0)
     return out
+
+
+class BackgroundCopy:
+    """Device -> host copies of a finished event chunk's layers on a worker thread, so that they overlap the next
+    chunk's fit (the staging slabs are shared: one BackgroundCopy at a time, `wait()` before the next starts)."""
+
+    def __init__(self, jobs, device):
+        import threading
+        self.error = None
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))      # the producers of every src are enqueued before this point
+
+        def run():
+            try:
+                torch.cuda.set_device(device)
+                for src, dst, col0 in jobs:
+                    to_host_columns(src, dst, col0, after=ev)
+            except BaseException as e:                     # surfaced by wait()
+                self.error = e
+        self.thread = threading.Thread(target=run, name="brie-d2h", daemon=True)
+        self.thread.start()
+
+    def wait(self):
+        self.thread.join()
+        if self.error is not None:
+            raise self.error

@@ -7,7 +7,7 @@ import pytest
 
 import oracle.brie2_oracle as ob
 from oracle.brie2_oracle import oracle_fit_matrix
-from util import device_eps_provider, make_lrt_problem, make_problem
+from util import bar_report, device_eps_provider, make_lrt_problem, make_problem
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
@@ -55,8 +55,10 @@ def test_fitBRIE_groups_match_sequential_reference_batches():
     gain = np.concatenate([r.ELBO_gain for r in refs], axis=0)
     fdr = np.concatenate([r.fdr for r in refs], axis=0)              # BH per batch, as the reference
     assert np.array_equal(res.fdr < 0.05, fdr < 0.05) and np.abs(res.fdr - fdr).max() < 5e-3
-    assert np.quantile(np.abs(res.Psi - Psi), 0.99) < 1e-3
+    n_psi = bar_report("fitBRIE groups Psi", np.abs(res.Psi - Psi), 1e-3)
+    assert n_psi <= 0.01 * Psi.size and np.quantile(np.abs(res.Psi - Psi), 0.99) < 1e-3
     big = np.abs(gain) > 1.5
+    bar_report("fitBRIE groups ELBO_gain (relative, |gain| > 1.5)", (np.abs(res.ELBO_gain - gain) / np.maximum(np.abs(gain), 1e-30))[big], 1e-3)
     assert (np.abs(res.ELBO_gain - gain)[big] / np.abs(gain)[big]).max() < 1e-3
     # uns['brie_losses'] = per-batch traces appended end to end (model_wrap.py:61)
     want = np.concatenate([r.losses for r in refs])
@@ -182,7 +184,8 @@ def test_device_simulator_statistics_and_engine_zero_copy():
     dev = simulate_counts_device(Nc, Ng, design='binary1', seed=5)
     host = simulate_counts(Nc, Ng, design='binary1', seed=5)          # different RNG streams, same distributions
     d = [t[:, :Ng].cpu().numpy() for t in dev['layers']]
-    assert dev['layers'][0].shape == (Nc, 224) and float(dev['layers'][0][:, Ng:].abs().max()) == 0.0
+    from brie_b200._lib import leading_dim
+    assert dev['layers'][0].shape == (Nc, leading_dim(Ng)) and float(dev['layers'][0][:, Ng:].abs().max()) == 0.0
     nz_d = (d[0] + d[1] + d[2] > 0)
     # pseudo-count applied exactly where c1 + c2 > 0
     frac = d[0] - np.floor(d[0])

@@ -13,7 +13,7 @@ import pytest
 from oracle import philox_np as px
 from oracle.brie2_oracle import OracleBRIE2, OracleInit, add_pseudo_count, oracle_fit_matrix
 
-from util import device_eps_provider, make_lrt_problem, make_problem
+from util import bar_report, device_eps_provider, make_lrt_problem, make_problem
 
 pytestmark = pytest.mark.gpu
 
@@ -220,6 +220,12 @@ def test_full_fit_with_lrt_matches_oracle(kind):
     envelope = np.abs(ref.Psi - ref64.Psi).max()
     print("Psi: q99.9 %.2e max %.2e | f32-vs-f64 oracle envelope %.2e | vs f64 %.2e" % (
         np.quantile(dpsi, 0.999), dpsi.max(), envelope, np.abs(res.Psi - ref64.Psi).max()))
+    # the strict bars, reported: Psi 1e-3 absolute on every element, ELBO_gain 1e-3 relative on every event
+    n_psi = bar_report("%s Psi" % kind, dpsi, 1e-3, np.abs(ref.Psi - ref64.Psi))
+    bar_report("%s ELBO_gain (relative, all events)" % kind,
+               np.abs(res.ELBO_gain - ref.ELBO_gain) / np.maximum(np.abs(ref.ELBO_gain), 1e-30), 1e-3,
+               np.abs(ref.ELBO_gain - ref64.ELBO_gain) / np.maximum(np.abs(ref64.ELBO_gain), 1e-30))
+    assert n_psi <= max(5, 2 * int((np.abs(ref.Psi - ref64.Psi) > 1e-3).sum()))      # as many as float32 itself produces
     assert np.quantile(dpsi, 0.95) < 1e-3 and np.median(dpsi) < 1e-4
     assert dpsi.max() <= max(1e-3, envelope)                      # as close as float32 itself allows
     assert np.abs(res.Psi - ref64.Psi).max() <= max(1e-3, 2 * envelope)

@@ -55,3 +55,19 @@ def make_lrt_problem(Nc=150, Ng=48, seed=8):
     c2 = rng.binomial(n - c1, p2 / (D - p1))
     c3 = n - c1 - c2
     return [c1.astype(np.float32), c2.astype(np.float32), c3.astype(np.float32)], effLen, x[:, None], beta
+
+
+def bar_report(name, diff, bar, envelope=None):
+    """Print how many elements of `diff` exceed the north_star bar `bar` (next to the float32-vs-float64 oracle
+    envelope when given) and return that count: the tests report violators instead of widening a bar."""
+    diff = np.asarray(diff)
+    n_viol = int((diff > bar).sum())
+    msg = "%s: bar %.0e | max %.2e q99.9 %.2e median %.2e | violators %d of %d (%.4f %%)" % (
+        name, bar, diff.max(initial=0), np.quantile(diff, 0.999) if diff.size else 0, np.median(diff) if diff.size else 0,
+        n_viol, diff.size, 100.0 * n_viol / max(diff.size, 1))
+    if envelope is not None:
+        envelope = np.asarray(envelope)
+        msg += " | float32-vs-float64 oracle envelope: max %.2e, its own violators %d" % (
+            envelope.max(initial=0), int((envelope > bar).sum()))
+    print(msg)
+    return n_viol
