@@ -482,6 +482,11 @@ def main():
     M = len(c["masks"])
     (lo, hi), group, Ng = shard_of(ctx, HEAD)
 
+    # ---- the small shape first, from an idle GPU: C2 is a 25 ms burst whose clocks should not be those the long legs leave
+    shapes = None
+    if not args.no_shapes:
+        shapes = {"C2": shape_leg(ctx, "C2", max(K, 50), W)}
+
     # ---- headline: C3, strong scaling, device-resident
     eng, nz = build_engine(ctx, HEAD, lo, hi, Ng, group)
     sampler = ClockSampler(ctx.local)
@@ -510,9 +515,7 @@ def main():
     del eng
     torch.cuda.empty_cache()
 
-    shapes = None
     if not args.no_shapes:
-        shapes = {"C2": shape_leg(ctx, "C2", max(K, 50), W)}
         ev5 = min(SHAPES["C5"]["events"] // ctx.world, 2048) * ctx.world
         shapes["C5"] = shape_leg(ctx, "C5", min(K, 10), 3, events=ev5,
                                  note="per-GPU slab of %d events (the full 20 000 need 8 GPUs: 150 GB per GPU)" % (ev5 // ctx.world))

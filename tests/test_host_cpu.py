@@ -421,3 +421,46 @@ def test_engine_plan_splits_long_lrt_lists():
     assert [(p[0], p[1]) for p in plan] == [([[], [0]], [0, 1])]
     plan = _engine_plan([], [[0], [1], [2]], False, 'gene', max_models=2)
     assert [p[1] for p in plan] == [[0, 1], [2, 3]]
+
+
+def test_product_path_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under brie_b200/ may import, load or execute it (a product path
+    routed through the oracle or any CPU fallback would void every parity claim)."""
+    import glob
+    bad = []
+    for path in glob.glob(os.path.join(ROOT, "brie_b200", "**", "*"), recursive=True):
+        if not path.endswith((".py", ".cu", ".cuh", ".h")):
+            continue
+        txt = open(path, errors="ignore").read()
+        if re.search(r"^\s*(from|import)\s+oracle\b|oracle[./]brie2|oracle/_ref|philox_np", txt, flags=re.M):
+            bad.append(path)
+    assert not bad, bad
+    # and the fit refuses to run without a CUDA device instead of falling back
+    import torch
+    if not torch.cuda.is_available():
+        from brie_b200.models import fit_BRIE_matrix
+        with pytest.raises(RuntimeError, match="no CUDA device"):
+            fit_BRIE_matrix([np.ones((3, 4), np.float32), np.ones((3, 4), np.float32)])
+
+
+def test_bench_reference_arm_runs_and_mirrors_the_config():
+    """`bench.py --impl reference` (the restated reference on the host cores; only rank 0 works) prints one JSON line
+    with the contract's keys and the same `config` dict the GPU arm prints."""
+    import json
+    import subprocess
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+              "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["steps"] == 2 and line["warmup"] == 1 and line["n_gpus"] == 2
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.config_dict(2) and line["unit"] == bench.UNIT and line["metric"] == bench.METRIC
+    other = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                           capture_output=True, text=True, timeout=60, cwd=ROOT, env=dict(os.environ, RANK="1"))
+    assert other.returncode == 0 and other.stdout.strip() == ""            # ranks other than 0 exit without work
