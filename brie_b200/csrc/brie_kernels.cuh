@@ -9,7 +9,9 @@
 // counts per cell x event (HBM-bound).
 //
 // Layout: every (cells, events) array is row-major, events contiguous, leading
-// dimension ld (ld % 4 == 0).  A warp owns a 128-event row segment (lane = 4
+// dimension ld (ld % 4 == 0 is all the kernels need; the Python layer pads ld to 128
+// floats so that rows start 512-byte aligned, +2-5 % on B200, profiles/r2_ab_rpi_tma.md).
+// A warp owns a 128-event row segment (lane = 4
 // consecutive events, one 16-byte load per array), a CTA of 8 warps owns
 // rows_per_cta x 128 and walks its rows warp-interleaved.  Per-event sums over
 // cells live in registers and leave the CTA as one partial per row chunk
