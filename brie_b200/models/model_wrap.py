@@ -516,11 +516,16 @@ def fitBRIE(adata, Xc=None, Xg=None, intercept=None, intercept_mode='gene',
             res_list.append(_ResVal)
             print("[BRIE2] %d out %d genes done" % (min(e0 + chunk, hi) - lo, hi - lo))
         _land()
+        timing_rank = {}                   # BRIE_TIMING diagnostics of THIS rank's chunks (the merged result sums all ranks)
+        for _r in res_list:
+            for k, v in (getattr(_r, 'timing', None) or {}).items():
+                timing_rank[k] = timing_rank.get(k, 0.0) + v
         if world > 1:                      # per-event vectors: every rank gets all of them, in event order
             parts = [None] * world
             dist.all_gather_object(parts, res_list)
             res_list = [r for p in parts for r in p]
         ResVal = concate(res_list)
+        ResVal.timing_rank = timing_rank
         for k, v in store.finish().items():
             setattr(ResVal, k, v)
     elif world > 1:

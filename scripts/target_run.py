@@ -162,7 +162,7 @@ def main():
                   float_format='%.3e')
         t_write = time.time() - t2
     # ---- per-rank report
-    tm = getattr(res, 'timing', None) or {}
+    tm = getattr(res, 'timing_rank', None) or getattr(res, 'timing', None) or {}    # this rank's own phases / kernel times
     peak = bench.hbm_peak()[0]
     frac = None
     if tm.get("step_kernel_ms_sum"):
